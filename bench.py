@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- YOLOv2-tiny 416x416 images/s on 1/2/4/8 B200 (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            (N=1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3]): a global batch of 4096 synthetic images per step, cut into
+contiguous slices of 4096/N per GPU (weights replicated, no collective on the hot path, one
+final output gather to rank 0), each slice run as micro-batches of 512 through the resident
+fused network.  One "step" = one pass of the hot path over the 4096 images.
+
+  value  : images/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e    : images/s through the host-buffer C-ABI call (pinned host in -> H2D -> 9 fused blocks ->
+           D2H -> pinned host out), copies inside the timed region
+  roofline: the dominant kernel (block 7, 3x3x1024->1024 on 13x13, 42% of the summed per-layer
+           roofline), timed in situ with CUDA events around its launches inside the timed steps
+  cpu_baseline: the reference's own OpenBLAS engine (oracle/_ref, compiled unmodified) timed on
+           this box's host cores on a bounded sample -- a reported baseline, not the target
+
+  --impl reference : times that CPU reference alone (rank 0), same metric/unit/config.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dnn-inference-engine_b200")
+for p in (PKG, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "YOLOv2-tiny 416x416 images/sec"
+UNIT = "images/s"
+GFLOP_PER_IMAGE = [0.1495, 0.3987, 0.3987, 0.3987, 0.3987, 0.3987, 1.5949, 3.1898, 0.0433]
+HW_IN = [416, 208, 104, 52, 26, 13, 13, 13, 13]
+HW_OUT = [208, 104, 52, 26, 13, 13, 13, 13, 13]
+CH = [3, 16, 32, 64, 128, 256, 512, 1024, 1024, 125]
+KS = [3, 3, 3, 3, 3, 3, 3, 3, 1]
+
+
+def algorithmic_bytes(layer, batch, act_bytes):
+    """unpadded input once + post-pool output once + weights once per batch + scale/shift.
+    The network input is always fp32 and so is the final output."""
+    e_in = 4 if layer == 0 else act_bytes
+    e_out = 4 if layer == 8 else act_bytes
+    return (batch * (HW_IN[layer] ** 2 * CH[layer] * e_in + HW_OUT[layer] ** 2 * CH[layer + 1] * e_out)
+            + KS[layer] ** 2 * CH[layer] * CH[layer + 1] * act_bytes + 2 * CH[layer + 1] * 4)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def openblas_threads():
+    try:
+        import build as oracle_build
+        lib = ctypes.CDLL(oracle_build.scipy_openblas())
+        return int(lib.scipy_openblas_get_num_threads())
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(n_images, weights, seed=100):
+    """Times the reference CPU engine on n_images (batch 1 each, fresh graph per image, wall clock
+    around the run only, as proj3/__init__.py:24-26 does).  Returns (images/s, kind, cores, seconds)."""
+    import chain
+    from synth import build_yolov2tiny, make_images
+    backend, kind = ("ref_openblas", "reference") if chain.available("ref_openblas") else ("oracle", "port")
+    if backend == "oracle":
+        import build as oracle_build
+        oracle_build.build_oracle()
+    total = 0.0
+    for i in range(n_images):
+        img = make_images(1, seed=seed, start=i)
+        c = chain.Chain(backend)
+        build_yolov2tiny(c, img.shape, weights)
+        t0 = time.perf_counter()
+        c.run(img)
+        total += time.perf_counter() - t0
+    cores = openblas_threads() if backend == "ref_openblas" else (os.cpu_count() or 1)
+    return n_images / total, kind, cores, total
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from synth import make_weights
+    weights = make_weights(0)
+    sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_reference_rate(sample, weights)
+    t_total, n_total, kind, cores = 0.0, 0, "port", 1
+    for s in range(args.steps):
+        rate, kind, cores, secs = cpu_reference_rate(sample, weights, seed=100 + s * sample)
+        t_total += secs
+        n_total += sample
+    value = n_total / t_total
+    desc = "%d images per step, batch 1 each, proj3 OpenBLAS engine compiled unmodified (oracle/_ref)" % sample \
+        if kind == "reference" else "%d images per step through oracle/oracle.c" % sample
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, cpu=False):
+    return {"workload": "YOLOv2-tiny 416x416x3, random-init weights, global batch %d sharded over %d GPU(s), "
+                        "micro-batch %d (BASELINE configs[3])" % (args.global_batch, args.gpus, args.micro_batch),
+            "global_batch": args.global_batch, "micro_batch": args.micro_batch,
+            "precision": "f32 (CPU)" if cpu else args.precision,
+            "l2": "inputs larger than L2 (%.1f GB read per step per GPU)" %
+                  (args.global_batch / max(1, args.gpus) * 416 * 416 * 3 * 4 / 1e9),
+            "parallelism": "batch-sharded dp%d, weights replicated, final output gather" % args.gpus}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import _lib
+    from synth import CHANNELS, KSIZES, POOLS, make_weights
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:   # plain `python bench.py --gpus N`: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29591", os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    assert args.global_batch % world == 0
+    n_local = args.global_batch // world
+    mb = min(args.micro_batch, n_local)
+    assert n_local % mb == 0
+    n_mb = n_local // mb
+
+    weights = make_weights(0)
+    spec = []
+    for i, w in enumerate(weights):
+        blk = {"kernel": w["kernel"], "padding": "SAME", "biases": w["biases"]}
+        if "gamma" in w:
+            blk.update(mean=w["moving_mean"], variance=w["moving_variance"], gamma=w["gamma"], epsilon=1e-5, leaky=True)
+        blk["pool"] = None if POOLS[i] is None else (POOLS[i][0], POOLS[i][1], "SAME")
+        spec.append(blk)
+    net = _lib.Net((mb, 416, 416, 3), spec, precision=args.precision, device=local_rank)
+    plan = [net.block_info(i) for i in range(net.num_blocks)]
+    act_bytes = 2 if args.precision == "bf16" else 4
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x = torch.rand((n_mb, mb, 416, 416, 3), device=dev, dtype=torch.float32, generator=gen)
+    y = torch.empty((n_mb, mb, 13, 13, 125), device=dev, dtype=torch.float32)
+    gathered = [torch.empty_like(y) for _ in range(world)] if (world > 1 and rank == 0) else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        for j in range(n_mb):
+            net.forward_device(x[j].data_ptr(), y[j].data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(y, gathered, dst=0)      # the only exchange: final output gather
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    fence()
+    dom = 7
+    net.profile_block(dom)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    fence()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    dom_ms, dom_n = net.profile_read()
+    net.profile_block(-1)
+    assert bool(torch.isfinite(y).all()), "non-finite outputs"
+    value = args.global_batch * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed)
+    e2e = None
+    if not args.no_e2e:
+        hin = _lib.PinnedArray((n_mb, mb, 416, 416, 3))
+        hout = _lib.PinnedArray((n_mb, mb, 13, 13, 125))
+        for j in range(n_mb):
+            hin.array[j] = x[j].cpu().numpy()
+
+        def e2e_step():
+            for j in range(n_mb):
+                net.forward_async(hin.array[j], hout.array[j])
+            net.sync()
+
+        e2e_step()
+        k_e2e = max(2, min(args.steps, 5))
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        fence()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ref_out = y[n_mb - 1].cpu().numpy()
+        same = bool(np.array_equal(ref_out, hout.array[n_mb - 1]))
+        e2e = {"value": args.global_batch * k_e2e / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(args.global_batch * 416 * 416 * 3 * 4),
+               "d2h_bytes_per_step": int(args.global_batch * 13 * 13 * 125 * 4),
+               "steps": k_e2e, "matches_device_path": same,
+               "note": "per micro-batch: cudaMemcpyAsync H2D -> 9 fused blocks -> cudaMemcpyAsync D2H on one stream"}
+        hin.free(); hout.free()
+
+    # ---- per-layer roofline (micro-batch, L2 flushed between repetitions)
+    peaks = measured_peaks()
+    layers = None
+    tensor_peak = None
+    if rank == 0:
+        tensor_peak = _lib.measure_mma_peak(args.precision, local_rank)
+        layer_ms = net.time_blocks(2, 5)
+        layers = []
+        for i, t in enumerate(layer_ms):
+            fl = GFLOP_PER_IMAGE[i] * 1e9 * mb
+            by = algorithmic_bytes(i, mb, act_bytes)
+            t_mem, t_tc = by / (peaks["hbm_gbs"] * 1e9), fl / (tensor_peak * 1e12)
+            bound = "hbm" if t_mem >= t_tc else "tensor"
+            layers.append({"layer": i, "kernel": plan[i]["kernel"], "ms": round(t, 4), "bound": bound,
+                           "gbs": round(by / (t * 1e-3) / 1e9, 1), "tflops": round(fl / (t * 1e-3) / 1e12, 1),
+                           "frac": round(max(t_mem, t_tc) / (t * 1e-3), 4)})
+
+    if rank == 0:
+        dom_flops = GFLOP_PER_IMAGE[dom] * 1e9 * mb
+        achieved = dom_flops / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_n else None
+        roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (block 7: 13x13x1024 -> 1024, 3x3, im2col TMA)",
+                    "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tensor_peak if achieved else None, "traffic": None,
+                    "peak_source": "measured on this box by dnnb_measure_mma_peak (tcgen05 kind::%s issue loop); "
+                                   "MEASURED_PEAKS.json (%s) holds bf16 cuBLAS %.1f TFLOP/s burst" %
+                                   ("tf32" if args.precision == "tf32" else "f16/bf16", peaks["source"], peaks["bf16_tflops"]),
+                    "launches_timed": dom_n, "avg_launch_ms": dom_ms / max(dom_n, 1),
+                    "share_of_step": dom_ms / total_ms if total_ms else None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, kind, cores, secs = cpu_reference_rate(args.cpu_sample, weights)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d images, batch 1 each, %.1f s of CPU time; proj3 OpenBLAS engine compiled unmodified, "
+                             "host has %d cpus" % (args.cpu_sample, secs, os.cpu_count() or 0)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+            "e2e": e2e, "gpu_launches": net.launches_per_forward() * n_mb * args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "layers": layers,
+            "sum_layer_roofline_frac": (sum(max(algorithmic_bytes(i, mb, act_bytes) / (peaks["hbm_gbs"] * 1e9),
+                                                 GFLOP_PER_IMAGE[i] * 1e9 * mb / (tensor_peak * 1e12)) for i in range(9))
+                                        / (sum(l["ms"] for l in layers) * 1e-3)) if layers else None,
+        }
+        print(json.dumps(line), flush=True)
+    net.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16"])
+    ap.add_argument("--global-batch", type=int, default=4096)
+    ap.add_argument("--micro-batch", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="images timed for cpu_baseline (about 10-30 s)")
+    ap.add_argument("--ref-sample", type=int, default=2, help="images per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,217 @@
+"""ctypes binding of libdnn_b200.so (include/dnn_b200.h).  The library is loaded by absolute
+path from next to this file (the reference loads './libdnn_X.so' relative to the cwd,
+proj3/dnn_openblas.py:9).  There is no fallback: a missing library is an ImportError, and a
+failing call raises RuntimeError with the library's message."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdnn_b200.so")
+
+TF32, BF16, FP32 = 0, 1, 2
+PRECISIONS = {"tf32": TF32, "bf16": BF16, "fp32": FP32}
+KERNEL_NAMES = {0: "simt", 1: "umma_tiled_pool", 2: "umma_im2col"}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(LIB_PATH + " is missing: build it with `python dnn-inference-engine_b200/build.py` "
+                      "(nvcc, sm_100a); this engine has no CPU fallback")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+FP = ctypes.POINTER(c_float)
+IP = ctypes.POINTER(c_int)
+
+lib.dnnb_last_error.restype = ctypes.c_char_p
+lib.dnnb_last_error.argtypes = []
+
+
+def _sig(name, *argtypes):
+    f = getattr(lib, name)
+    f.restype = c_int
+    f.argtypes = list(argtypes)
+    return f
+
+
+_sig("dnnb_version")
+_sig("dnnb_device_count", IP)
+_sig("conv2d_mul", FP, FP, FP, FP, *([c_int] * 11))
+_sig("bias_add", FP, FP, FP, *([c_int] * 4))
+_sig("batch_norm", FP, FP, FP, FP, c_float, FP, *([c_int] * 4))
+_sig("max_pool2d", FP, FP, *([c_int] * 11))
+_sig("leaky_relu", FP, FP, *([c_int] * 4))
+_sig("dnnb_net_create", c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p))
+_sig("dnnb_net_add_block", c_void_p, FP, c_int, c_int, c_int, c_int, c_int, FP, FP, FP, FP, c_float,
+     c_int, c_int, c_int, c_int)
+_sig("dnnb_net_finalize", c_void_p)
+_sig("dnnb_net_num_blocks", c_void_p, IP)
+_sig("dnnb_net_out_shape", c_void_p, IP, IP, IP, IP)
+_sig("dnnb_net_forward", c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_forward_async", c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_forward_device", c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_sync", c_void_p)
+_sig("dnnb_net_block_output", c_void_p, c_int, FP)
+_sig("dnnb_net_block_info", c_void_p, c_int, IP)
+_sig("dnnb_net_time_blocks", c_void_p, c_int, c_int, FP)
+_sig("dnnb_net_launches_per_forward", c_void_p, IP)
+_sig("dnnb_net_profile_block", c_void_p, c_int)
+_sig("dnnb_net_profile_read", c_void_p, FP, IP)
+_sig("dnnb_net_destroy", c_void_p)
+_sig("dnnb_host_alloc", c_size_t, ctypes.POINTER(c_void_p))
+_sig("dnnb_host_free", c_void_p)
+_sig("dnnb_measure_mma_peak", c_int, c_int, FP)
+
+EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
+           "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
+           "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
+           "dnnb_net_forward_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info",
+           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
+           "dnnb_host_free", "dnnb_measure_mma_peak"]
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("libdnn_b200: " + lib.dnnb_last_error().decode("utf-8", "replace"))
+
+
+def fptr(a):
+    return a.ctypes.data_as(FP)
+
+
+def f32c(a):
+    """float32, C-contiguous view/copy (the reference hands numpy buffers to C as float*)."""
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def device_count():
+    n = c_int(0)
+    check(lib.dnnb_device_count(ctypes.byref(n)))
+    return n.value
+
+
+class PinnedArray:
+    """A float32 numpy array over page-locked host memory (async H2D/D2H)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self.shape))
+        self._ptr = c_void_p()
+        check(lib.dnnb_host_alloc(n * 4, ctypes.byref(self._ptr)))
+        buf = (c_float * n).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            lib.dnnb_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Net:
+    """Resident fused network (dnnb_net_*).  blocks: list of dicts with keys kernel, padding,
+    biases, mean, variance, gamma, epsilon, leaky, pool (None or (k, s, padding))."""
+
+    def __init__(self, in_shape, blocks, precision="tf32", device=0):
+        b, h, w, c = (int(v) for v in in_shape)
+        self.in_shape = (b, h, w, c)
+        self.precision = precision
+        self.device = device
+        self._h = c_void_p()
+        check(lib.dnnb_net_create(device, PRECISIONS[precision], b, h, w, c, ctypes.byref(self._h)))
+        try:
+            for blk in blocks:
+                k = f32c(blk["kernel"])
+                kh, kw, ic, oc = k.shape
+                opt = lambda key: None if blk.get(key) is None else f32c(blk[key])
+                bias, mean, var, gamma = opt("biases"), opt("mean"), opt("variance"), opt("gamma")
+                p = lambda a: None if a is None else fptr(a)
+                pool = blk.get("pool")
+                pk, ps, pp = (0, 0, 1) if pool is None else (pool[0], pool[1], 1 if pool[2] == 'SAME' else 0)
+                check(lib.dnnb_net_add_block(self._h, fptr(k), kh, kw, ic, oc, 1 if blk.get("padding", 'SAME') == 'SAME' else 0,
+                                             p(bias), p(mean), p(var), p(gamma), float(blk.get("epsilon", 0.0)),
+                                             1 if blk.get("leaky") else 0, pk, ps, pp))
+            check(lib.dnnb_net_finalize(self._h))
+            o = [c_int(0) for _ in range(4)]
+            check(lib.dnnb_net_out_shape(self._h, *[ctypes.byref(v) for v in o]))
+            self.out_shape = tuple(v.value for v in o)
+            n = c_int(0)
+            check(lib.dnnb_net_num_blocks(self._h, ctypes.byref(n)))
+            self.num_blocks = n.value
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib.dnnb_net_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, x, out=None):
+        x = f32c(x)
+        assert tuple(x.shape) == self.in_shape, (x.shape, self.in_shape)
+        if out is None:
+            out = np.empty(self.out_shape, dtype=np.float32)
+        check(lib.dnnb_net_forward(self._h, x.ctypes.data, out.ctypes.data))
+        return out
+
+    def forward_async(self, x, out):
+        """x, out: C-contiguous float32 arrays (ideally PinnedArray.array) kept alive until sync()."""
+        check(lib.dnnb_net_forward_async(self._h, x.ctypes.data, out.ctypes.data))
+
+    def forward_device(self, in_ptr, out_ptr=None, stream=None):
+        check(lib.dnnb_net_forward_device(self._h, in_ptr, out_ptr, stream))
+
+    def sync(self):
+        check(lib.dnnb_net_sync(self._h))
+
+    def block_info(self, i):
+        info = (c_int * 12)()
+        check(lib.dnnb_net_block_info(self._h, i, info))
+        v = list(info)
+        return {"kernel": KERNEL_NAMES[v[0]], "out_shape": (self.in_shape[0], v[1], v[2], v[3]),
+                "pool_fused": bool(v[4]), "bn_tile": v[5], "swizzle": v[6], "stages": v[7], "grid": v[8],
+                "pool_separate": bool(v[9]), "act_bytes": v[10], "launches": v[11]}
+
+    def block_output(self, i):
+        shape = self.block_info(i)["out_shape"]
+        out = np.empty(shape, dtype=np.float32)
+        check(lib.dnnb_net_block_output(self._h, i, fptr(out)))
+        return out
+
+    def time_blocks(self, warmup=3, iters=10):
+        ms = (c_float * self.num_blocks)()
+        check(lib.dnnb_net_time_blocks(self._h, warmup, iters, ms))
+        return list(ms)
+
+    def profile_block(self, block):
+        check(lib.dnnb_net_profile_block(self._h, block))
+
+    def profile_read(self):
+        ms, n = c_float(0), c_int(0)
+        check(lib.dnnb_net_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def launches_per_forward(self):
+        n = c_int(0)
+        check(lib.dnnb_net_launches_per_forward(self._h, ctypes.byref(n)))
+        return n.value
+
+
+def measure_mma_peak(precision="tf32", device=0):
+    t = c_float(0)
+    check(lib.dnnb_measure_mma_peak(device, PRECISIONS[precision], ctypes.byref(t)))
+    return t.value

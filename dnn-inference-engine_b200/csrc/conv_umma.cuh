@@ -1,0 +1,390 @@
+// conv_umma.cuh -- the hot kernel: NHWC stride-1 convolution as an implicit GEMM on the
+// sm_100a tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands staged by TMA,
+// with bias + folded BatchNorm + LeakyReLU(0.1) (+ the 2x2/2 max-pool) fused in the epilogue.
+// Replaces, for one conv block of proj3/yolov2tiny.py:30-77, the reference's
+// np.pad -> im2col -> sgemm -> bias_add -> batch_norm -> leaky_relu -> np.pad -> max_pool2d
+// chain (proj3/dnn_openblas.py:174-284, proj3/dnn_openblas.c:9-254).
+//
+// GEMM view: D[m][n] = sum_k A[m][k] * Wt[n][k], m = output pixel, n = output channel,
+// k = (filter tap, input channel).  One K-block = one tap x BKC channels, where BKC channels
+// are SWZ bytes (one swizzle span) of an NHWC pixel.  No im2col matrix ever exists: the A tile
+// of a K-block is fetched straight from the activation tensor by one TMA request,
+//   * tiled mode : a [nb, th, tw, BKC] box whose (h, w) origin is shifted by the tap; rows that
+//                  fall outside the image are zero-filled by TMA = SAME padding.  The 128 rows
+//                  of a tile form whole 2x2 pooling windows, so the pool is fused.
+//   * im2col mode: 128 consecutive output pixels (running over rows and images) through a
+//                  cuTensorMapEncodeIm2col descriptor; used for the 13x13 layers, whose M
+//                  would otherwise not tile without waste.
+// Weights are prepacked once as [tap][OCp][ICp] (K-major), so the B tile is one 3-D TMA box.
+//
+// CTA = 192 threads, persistent over tiles (static round-robin):
+//   warp 0   : TMA producer (one elected lane)          full/empty mbarrier ring, STAGES deep
+//   warp 1   : TMEM allocator + MMA issuer (one lane)   tcgen05.mma cta_group::1, M=128, N=BN
+//   warps 2-5: epilogue, one TMEM lane quarter each     2 accumulator stages (tmem_full/empty)
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace umma_conv {
+
+constexpr int kThreads = 192;
+constexpr int kBM = 128;
+
+struct Params {
+    int H, W, B;          // conv output = input spatial size (stride 1, SAME)
+    int OC;               // real output channels (columns beyond are dropped)
+    int KH, KW, PT, PL;   // filter and top/left padding
+    int c_chunks;         // K-blocks per tap = ICp / BKC
+    int num_m_tiles, num_n_tiles;
+    // tiled mode: tile = nb images x th rows x tw cols (all powers of two, product 128)
+    int tw, th, nb, log2_tw, log2_th, tiles_w, tiles_h;
+    int M_total;          // im2col mode: B*H*W
+    const float *scale;   // [num_n_tiles*BN]  gamma / sqrt(var + eps)      (1 when no BN)
+    const float *shift;   // [num_n_tiles*BN]  (bias - mean) * scale         (bias when no BN)
+    void *out;            // [B, OH, OW, OC]
+    int OH, OW;           // stored spatial size (H/2, W/2 when the pool is fused)
+    int leaky;
+    int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
+};
+
+template <int BN, int SWZ, int KBS>
+struct Cfg {
+    static constexpr int A_TILE = kBM * SWZ;
+    static constexpr int B_TILE = BN * SWZ;
+    static constexpr int STAGE_BYTES = KBS * (A_TILE + B_TILE);
+    static constexpr int TAIL_BYTES = 1024 /*barriers+tmem slot*/ + 2 * 1024 * 4 /*scale, shift*/;
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/;
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - TAIL_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static_assert(STAGES >= 2, "pipeline needs at least two stages");
+    static_assert(TMEM_COLS <= 512, "two accumulator stages must fit TMEM");
+};
+
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const Params p) {
+    using C = Cfg<BN, SWZ, KBS>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int ES = BF16 ? 2 : 4;
+    constexpr int BKC = SWZ / ES;            // channels per K-block
+    constexpr int MMA_PER_KB = SWZ / 32;     // each MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
+    static_assert(!(POOL && IM2COL), "the fused pool needs spatial tiles");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tail = smem + STAGES * C::STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);           // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
+    float *s_scale = reinterpret_cast<float *>(tail + 1024);
+    float *s_shift = s_scale + 1024;
+
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t bar_full = ptx::smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES;
+    const uint32_t bar_tempty = bar_tfull + 16;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int taps = p.KH * p.KW;
+    const int num_kstages = taps * p.c_chunks / KBS;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(bar_full + 8 * s, 1);
+            ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(bar_tfull + 8 * s, 1);
+            ptx::mbar_init(bar_tempty + 8 * s, 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    for (int i = threadIdx.x; i < p.num_n_tiles * BN; i += kThreads) {
+        s_scale[i] = p.scale[i];
+        s_shift[i] = p.shift[i];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                const int m_tile = tile / p.num_n_tiles;
+                int w0, h0, n0;
+                if constexpr (IM2COL) {
+                    const int m0 = m_tile * kBM;
+                    n0 = m0 / (p.H * p.W);
+                    const int rem = m0 - n0 * (p.H * p.W);
+                    h0 = rem / p.W;
+                    w0 = rem - h0 * p.W;
+                } else {
+                    w0 = (m_tile % p.tiles_w) * p.tw;
+                    h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                    n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                }
+                for (int ks = 0; ks < num_kstages; ++ks) {
+                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    ptx::mbar_expect_tx(full, C::STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + KBS * C::A_TILE;
+#pragma unroll
+                    for (int j = 0; j < KBS; ++j) {
+                        const int kb = ks * KBS + j;
+                        const int tap = kb / p.c_chunks;
+                        const int cc = kb - tap * p.c_chunks;
+                        const int di = tap / p.KW, dj = tap - di * p.KW;
+                        if constexpr (IM2COL)
+                            ptx::tma_load_im2col_4d(sa + j * C::A_TILE, &map_a, full, cc * BKC, w0 - p.PL, h0 - p.PT, n0,
+                                                    (uint16_t)dj, (uint16_t)di);
+                        else
+                            ptx::tma_load_4d(sa + j * C::A_TILE, &map_a, full, cc * BKC, w0 + dj - p.PL, h0 + di - p.PT, n0);
+                        ptx::tma_load_3d(sb + j * C::B_TILE, &map_b, full, cc * BKC, n_tile * BN, tap);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1u : 2u, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int ks = 0; ks < num_kstages; ++ks) {
+                    ptx::mbar_wait(bar_full + 8 * stage, phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + KBS * C::A_TILE;
+#pragma unroll
+                    for (int j = 0; j < KBS; ++j) {
+                        const uint64_t da = ptx::umma_desc_kmajor(sa + j * C::A_TILE, SWZ);
+                        const uint64_t db = ptx::umma_desc_kmajor(sb + j * C::B_TILE, SWZ);
+#pragma unroll
+                        for (int k = 0; k < MMA_PER_KB; ++k)
+                            ptx::umma<BF16>(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | j | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(bar_empty + 8 * stage);   // smem slot free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(bar_tfull + 8 * acc);          // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
+        const int row = quarter * 32 + lane;           // tile row = output pixel slot
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int n_tile = tile % p.num_n_tiles;
+            const int m_tile = tile / p.num_n_tiles;
+
+            bool valid;
+            size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
+            if constexpr (IM2COL) {
+                const int m = m_tile * kBM + row;
+                valid = m < p.M_total;
+                out_pix = (size_t)m;
+            } else {
+                const int w0 = (m_tile % p.tiles_w) * p.tw;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                const int wl = row & (p.tw - 1);
+                const int hl = (row >> p.log2_tw) & (p.th - 1);
+                const int nl = row >> (p.log2_tw + p.log2_th);
+                const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+                valid = n < p.B;
+                if constexpr (POOL) out_pix = ((size_t)n * p.OH + (h >> 1)) * p.OW + (w >> 1);
+                else out_pix = ((size_t)n * p.OH + h) * p.OW + w;
+            }
+
+            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            ptx::tc_fence_after();
+
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t raw[32];
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
+                ptx::tmem_ld_wait();
+                const int col0 = n_tile * BN + chunk * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
+                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j);
+                    v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
+                    v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
+                    v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
+                }
+                if (p.leaky) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                }
+                if constexpr (!OUT_BF16) {
+                    if (p.round_tf32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+                    }
+                } else {   // round before pooling: the reference pools the stored values
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                }
+
+                if constexpr (POOL) {
+                    // butterfly 2x2 max over lanes (w^1, then h^1 = lane ^ tw); each lane ends up
+                    // with 8 of the 32 columns of its window: 16*(w&1) + 8*(h&1) + [0,8)
+                    const bool wodd = lane & 1;
+                    float a[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float keep = wodd ? v[16 + j] : v[j];
+                        const float send = wodd ? v[j] : v[16 + j];
+                        a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                    }
+                    const bool hodd = (lane >> p.log2_tw) & 1;
+                    float r8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float keep = hodd ? a[8 + j] : a[j];
+                        const float send = hodd ? a[j] : a[8 + j];
+                        r8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tw));
+                    }
+                    const int col = col0 + (wodd ? 16 : 0) + (hodd ? 8 : 0);
+                    if (valid && col < p.OC) {
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col;
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]);
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(r8[2], r8[3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]);
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(r8[6], r8[7]);
+                            pk.x = *reinterpret_cast<uint32_t *>(&t0);
+                            pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&t2);
+                            pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                            *reinterpret_cast<uint4 *>(o) = pk;
+                        } else {
+                            float *o = static_cast<float *>(p.out) + out_pix * p.OC + col;
+                            *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+                            *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+                        }
+                    }
+                } else {
+                    if (valid) {
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col0;
+                            if ((p.OC & 7) == 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    if (col0 + j < p.OC) {
+                                        uint4 pk;
+                                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                                        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                                        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                        pk.x = *reinterpret_cast<uint32_t *>(&t0);
+                                        pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                                        pk.z = *reinterpret_cast<uint32_t *>(&t2);
+                                        pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                                        *reinterpret_cast<uint4 *>(o + j) = pk;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < p.OC) o[j] = __float2bfloat16_rn(v[j]);
+                            }
+                        } else {
+                            float *o = static_cast<float *>(p.out) + out_pix * p.OC + col0;
+                            if ((p.OC & 3) == 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    if (col0 + j < p.OC)
+                                        *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < p.OC) o[j] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe peak probe: every CTA issues `iters` x (128 x 256 x 32B-of-K) MMAs back to back
+// on resident (zeroed) shared memory, no loads, no epilogue.
+template <bool BF16>
+__global__ void __launch_bounds__(64, 1) mma_peak_kernel(int iters) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    const uint32_t b = ptx::smem_u32(&bar);
+    if (threadIdx.x == 0) { ptx::mbar_init(b, 1); ptx::fence_barrier_init(); }
+    if (threadIdx.x < 32) ptx::tmem_alloc(ptx::smem_u32(&slot), 512);
+    // generic-proxy writes above must be visible to the async proxy (UMMA reads smem)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1u : 2u, 256);
+        const uint64_t da = ptx::umma_desc_kmajor(ptx::smem_u32(smem), 128);
+        const uint64_t db = ptx::umma_desc_kmajor(ptx::smem_u32(smem) + A_BYTES, 128);
+        uint32_t phase = 0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma<BF16>(tmem + (it & 1) * 256, da + 2 * k, db + 2 * k, idesc, 1u);
+            if ((it & 31) == 31 || it == iters - 1) {
+                ptx::umma_commit(b);
+                ptx::mbar_wait(b, phase);
+                phase ^= 1;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace umma_conv

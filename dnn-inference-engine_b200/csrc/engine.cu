@@ -1,0 +1,936 @@
+// engine.cu -- libdnn_b200.so: the C ABI declared in include/dnn_b200.h.
+//   * op-level entry points with the reference's signatures (proj3/dnn_openblas.c)
+//   * the resident network: per-block kernel planning, weight prepack, TMA descriptors,
+//     HBM-resident activations, the forward launch sequence.
+// Host-side only; the kernels live in conv_umma.cuh (tcgen05/TMA) and ops_simt.cuh.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dnn_b200.h"
+#include "conv_umma.cuh"
+#include "ops_simt.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(...)                                                                                       \
+    do {                                                                                              \
+        cudaError_t e_ = (__VA_ARGS__);                                                                    \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail("%s:%d: %s -> %s", __FILE__, __LINE__, #__VA_ARGS__, cudaGetErrorString(e_));        \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// driver entry points for tensor-map encoding (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_fns() {
+    if (g_encode_tiled && g_encode_im2col) return 0;
+    cudaDriverEntryPointQueryResult q;
+    void *f = nullptr;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f);
+    f = nullptr;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeIm2col not available");
+    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f);
+    return 0;
+}
+
+CUtensorMapSwizzle swizzle_enum(int swz) {
+    return swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side rounding used by the weight prepack (round to nearest even)
+float host_round_tf32(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0xfffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+uint16_t host_bf16(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+void out_pads(int in_size, int k, int s, int same, int *o, int *pf, int *pb) {
+    // TF SAME / VALID, proj3/dnn_openblas.py:127-142
+    if (same) {
+        *o = (in_size + s - 1) / s;
+        int pad = (*o - 1) * s + k - in_size;
+        if (pad < 0) pad = 0;
+        *pf = pad / 2;
+        *pb = pad - pad / 2;
+    } else {
+        *o = (in_size - k + 1 + s - 1) / s;
+        *pf = *pb = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 kernel instantiations and their dispatch table
+typedef cudaError_t (*UmmaLauncher)(const CUtensorMap &, const CUtensorMap &, const umma_conv::Params &, int grid,
+                                    cudaStream_t);
+struct UmmaKey {
+    bool bf16, out_bf16;
+    int bn, swz, kbs;
+    bool im2col, pool;
+};
+struct UmmaEntry {
+    UmmaKey key;
+    UmmaLauncher launch;
+    int stages, smem;
+};
+
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL>
+cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
+                        cudaStream_t st) {
+    using C = umma_conv::Cfg<BN, SWZ, KBS>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL>;
+    static bool configured = false;   // per process; every device of one box is the same part
+    static int configured_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured || configured_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+        configured_dev = dev;
+    }
+    kern<<<grid, umma_conv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);
+    return cudaGetLastError();
+}
+
+#define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL)                                      \
+    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL>, \
+     umma_conv::Cfg<BN, SWZ, KBS>::STAGES, umma_conv::Cfg<BN, SWZ, KBS>::SMEM_BYTES}
+
+const UmmaEntry g_umma_table[] = {
+    // TF32 operands (fp32 storage in and out)
+    UMMA_ENTRY(false, false, 32, 64, 3, false, true),
+    UMMA_ENTRY(false, false, 64, 128, 1, false, true),
+    UMMA_ENTRY(false, false, 128, 128, 1, false, true),
+    UMMA_ENTRY(false, false, 256, 128, 1, false, true),
+    UMMA_ENTRY(false, false, 256, 128, 1, true, false),
+    UMMA_ENTRY(false, false, 128, 128, 1, true, false),
+    // BF16 operands, bf16 storage out
+    UMMA_ENTRY(true, true, 32, 32, 3, false, true),
+    UMMA_ENTRY(true, true, 64, 64, 3, false, true),
+    UMMA_ENTRY(true, true, 128, 128, 1, false, true),
+    UMMA_ENTRY(true, true, 256, 128, 1, false, true),
+    UMMA_ENTRY(true, true, 256, 128, 1, true, false),
+    UMMA_ENTRY(true, true, 128, 128, 1, true, false),
+    // BF16 operands, fp32 out (a network's last block)
+    UMMA_ENTRY(true, false, 32, 32, 3, false, true),
+    UMMA_ENTRY(true, false, 64, 64, 3, false, true),
+    UMMA_ENTRY(true, false, 128, 128, 1, false, true),
+    UMMA_ENTRY(true, false, 256, 128, 1, false, true),
+    UMMA_ENTRY(true, false, 256, 128, 1, true, false),
+    UMMA_ENTRY(true, false, 128, 128, 1, true, false),
+};
+
+const UmmaEntry *find_umma(const UmmaKey &k) {
+    for (const UmmaEntry &e : g_umma_table)
+        if (e.key.bf16 == k.bf16 && e.key.out_bf16 == k.out_bf16 && e.key.bn == k.bn && e.key.swz == k.swz &&
+            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool)
+            return &e;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+struct Block {
+    // description
+    int kh = 0, kw = 0, ic = 0, oc = 0, same = 1;
+    bool has_bn = false, leaky = false;
+    int pool_k = 0, pool_s = 0, pool_same = 1;
+    std::vector<float> kernel, scale, shift;   // HWIO fp32; folded epilogue constants [oc]
+    // geometry
+    int ih = 0, iw = 0;                         // input spatial
+    int ch = 0, cw = 0, pt = 0, pl = 0;         // conv output spatial, top/left pad
+    int oh = 0, ow = 0, ppt = 0, ppl = 0;       // block output spatial (after pool), pool pads
+    // plan
+    int family = DNNB_KERNEL_SIMT;
+    bool pool_fused = false, pool_separate = false;
+    bool in_bf16 = false, out_bf16 = false;     // storage types
+    bool round_tf32 = false;
+    const UmmaEntry *umma = nullptr;
+    umma_conv::Params up{};
+    CUtensorMap map_a{}, map_b{};
+    const void *map_a_base = nullptr;           // input pointer the A map was encoded for
+    int bn = 0, swz = 0, grid = 0;
+    // device memory
+    float *d_kernel = nullptr;                  // HWIO fp32 (SIMT)
+    void *d_wpack = nullptr;                    // [tap][OCp][IC] tf32-rounded fp32 or bf16
+    float *d_scale = nullptr, *d_shift = nullptr;
+    void *d_conv_out = nullptr;                 // conv(+fused pool) output
+    void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
+    size_t conv_out_elems = 0, out_elems = 0;
+};
+
+}  // namespace
+
+struct dnnb_net {
+    int device = 0, precision = DNNB_TF32;
+    int B = 0, H = 0, W = 0, C = 0;
+    std::vector<Block> blocks;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    float *d_in = nullptr;        // fp32 staging of the host input
+    void *d_in_cast = nullptr;    // input in the first tcgen05 block's storage type
+    float *d_out_f32 = nullptr;   // fp32 copy of the last output when it is stored as bf16
+    void *d_flush = nullptr;      // L2 flush scratch for dnnb_net_time_blocks
+    int num_sms = 148;
+    int launches = 0;
+    // optional in-situ timing of one block (bench.py's roofline leg): event pairs recorded
+    // around that block's kernels on whatever stream the forward runs on
+    int prof_block = -1;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
+    const int es = b.in_bf16 ? 2 : 4;
+    const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[4] = {(cuuint64_t)b.ic, (cuuint64_t)b.iw, (cuuint64_t)b.ih, (cuuint64_t)net->B};
+    cuuint64_t strides[3] = {(cuuint64_t)b.ic * es, (cuuint64_t)b.iw * b.ic * es, (cuuint64_t)b.ih * b.iw * b.ic * es};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const int bkc = b.swz / es;
+    CUresult r;
+    if (b.family == DNNB_KERNEL_UMMA_IM2COL) {
+        int lower[2] = {-b.pl, -b.pt};
+        int upper[2] = {(b.kw - 1 - b.pl) - (b.kw - 1), (b.kh - 1 - b.pt) - (b.kh - 1)};   // pad_back - (k-1)
+        r = g_encode_im2col(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper, (cuuint32_t)bkc,
+                            (cuuint32_t)umma_conv::kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz),
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)b.up.tw, (cuuint32_t)b.up.th, (cuuint32_t)b.up.nb};
+        r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail("tensor-map encode (A, family %d) failed: CUresult %d", b.family, (int)r);
+    b.map_a_base = in_ptr;
+    return 0;
+}
+
+int encode_map_b(Block &b) {
+    const int es = b.in_bf16 ? 2 : 4;
+    const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const int ocp = b.up.num_n_tiles * b.bn;
+    cuuint64_t dims[3] = {(cuuint64_t)b.ic, (cuuint64_t)ocp, (cuuint64_t)(b.kh * b.kw)};
+    cuuint64_t strides[2] = {(cuuint64_t)b.ic * es, (cuuint64_t)ocp * b.ic * es};
+    cuuint32_t box[3] = {(cuuint32_t)(b.swz / es), (cuuint32_t)b.bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(&b.map_b, dt, 3, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("tensor-map encode (weights) failed: CUresult %d", (int)r);
+    return 0;
+}
+
+// Decide how block `i` runs.  in_bf16: storage type of its input.
+void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
+    Block &b = net->blocks[i];
+    const bool last = i + 1 == net->blocks.size();
+    const bool want_bf16 = net->precision == DNNB_BF16;
+    b.in_bf16 = in_bf16;
+    b.out_bf16 = want_bf16 && !last;
+    b.round_tf32 = net->precision == DNNB_TF32 && !last;
+    b.family = DNNB_KERNEL_SIMT;
+    b.pool_fused = false;
+    const bool force_simt = getenv("DNNB_FORCE_SIMT") != nullptr;
+
+    if (net->precision != DNNB_FP32 && !force_simt && b.same && b.ch == b.ih && b.cw == b.iw) {
+        const int es = in_bf16 ? 2 : 4;
+        const int row_bytes = b.ic * es;
+        const int swz = row_bytes >= 128 ? 128 : row_bytes;
+        const bool k_ok = (row_bytes == 32 || row_bytes == 64 || row_bytes % 128 == 0);
+        const int bn = b.oc <= 32 ? 32 : b.oc <= 64 ? 64 : b.oc <= 128 ? 128 : 256;
+        const int ocp = round_up(b.oc, bn);
+        const int c_chunks = row_bytes / swz;
+        const int total_kb = b.kh * b.kw * c_chunks;
+        const int kbs = (swz < 128 && total_kb % 3 == 0) ? 3 : 1;
+        if (k_ok && ocp <= 1024) {
+            // fused pool geometry: tile = nb x th x tw, powers of two, product 128, tw <= 16, th >= 2
+            bool fuse = b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0 && b.oc % 8 == 0;
+            int tw = 1, th = 1, nb = 1;
+            if (fuse) {
+                while (tw < 16 && b.iw % (tw * 2) == 0) tw *= 2;
+                while (tw * th < 128 && b.ih % (th * 2) == 0) th *= 2;
+                nb = 128 / (tw * th);
+                fuse = tw >= 2 && th >= 2;
+            }
+            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse};
+            const UmmaEntry *e = find_umma(key);
+            if (e) {
+                b.umma = e;
+                b.family = fuse ? DNNB_KERNEL_UMMA_TILED : DNNB_KERNEL_UMMA_IM2COL;
+                b.pool_fused = fuse;
+                b.bn = bn;
+                b.swz = swz;
+                umma_conv::Params &p = b.up;
+                p = umma_conv::Params{};
+                p.H = b.ih; p.W = b.iw; p.B = net->B; p.OC = b.oc;
+                p.KH = b.kh; p.KW = b.kw; p.PT = b.pt; p.PL = b.pl;
+                p.c_chunks = c_chunks;
+                p.num_n_tiles = ocp / bn;
+                if (fuse) {
+                    p.tw = tw; p.th = th; p.nb = nb; p.log2_tw = ilog2(tw); p.log2_th = ilog2(th);
+                    p.tiles_w = b.iw / tw; p.tiles_h = b.ih / th;
+                    p.num_m_tiles = p.tiles_w * p.tiles_h * ((net->B + nb - 1) / nb);
+                    p.OH = b.ih / 2; p.OW = b.iw / 2;
+                } else {
+                    p.tw = p.th = p.nb = 1;
+                    p.M_total = net->B * b.ih * b.iw;
+                    p.num_m_tiles = (p.M_total + umma_conv::kBM - 1) / umma_conv::kBM;
+                    p.OH = b.ih; p.OW = b.iw;
+                }
+                p.leaky = b.leaky;
+                p.round_tf32 = b.round_tf32;
+                const int tiles = p.num_m_tiles * p.num_n_tiles;
+                b.grid = tiles < net->num_sms ? tiles : net->num_sms;
+            }
+        }
+    }
+    if (b.family == DNNB_KERNEL_SIMT)
+        b.pool_fused = b.pool_k == 2 && b.pool_s == 2 && b.ch % 2 == 0 && b.cw % 2 == 0;
+    b.pool_separate = b.pool_k > 0 && !b.pool_fused;
+}
+
+template <typename TIn, typename TOut>
+cudaError_t launch_simt_conv(const simt::ConvParams &p, cudaStream_t st) {
+    dim3 grid((unsigned)(p.B * p.tiles_y * p.tiles_x), (unsigned)((p.OC + 63) / 64));
+    simt::conv_fused_kernel<TIn, TOut><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t run_simt_conv(const simt::ConvParams &p, bool in_bf16, bool out_bf16, cudaStream_t st) {
+    if (in_bf16) return out_bf16 ? launch_simt_conv<__nv_bfloat16, __nv_bfloat16>(p, st) : launch_simt_conv<__nv_bfloat16, float>(p, st);
+    return out_bf16 ? launch_simt_conv<float, __nv_bfloat16>(p, st) : launch_simt_conv<float, float>(p, st);
+}
+
+int ew_grid(size_t n, int num_sms) {
+    size_t blocks = (n + 255) / 256;
+    size_t cap = (size_t)num_sms * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+cudaError_t run_pool(const simt::PoolParams &p, bool bf16, int num_sms, cudaStream_t st) {
+    const size_t n = (size_t)p.B * p.OH * p.OW * p.C;
+    const int grid = ew_grid(n, num_sms);
+    if (bf16) simt::maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    else simt::maxpool_kernel<float><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// launches the kernels of one block; `in` has the block's input storage type
+int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override, cudaStream_t st) {
+    void *conv_out = b.d_conv_out;
+    void *out = final_out_override ? final_out_override : b.d_out;
+    if (!b.pool_separate) conv_out = out;
+    if (b.family == DNNB_KERNEL_SIMT) {
+        simt::ConvParams p{};
+        p.in = in; p.w = b.d_kernel; p.out = conv_out; p.scale = b.d_scale; p.shift = b.d_shift;
+        p.B = net->B; p.IH = b.ih; p.IW = b.iw; p.IC = b.ic; p.OH = b.ch; p.OW = b.cw; p.OC = b.oc;
+        p.KH = b.kh; p.KW = b.kw; p.SH = 1; p.SW = 1; p.PT = b.pt; p.PL = b.pl;
+        p.leaky = b.leaky; p.pool = b.pool_fused; p.round_tf32 = b.round_tf32;
+        p.tiles_y = (b.ch + 7) / 8; p.tiles_x = (b.cw + 7) / 8;
+        CK(run_simt_conv(p, b.in_bf16, b.out_bf16, st));
+    } else {
+        if (b.map_a_base != in) {
+            if (encode_map_a(net, b, in)) return 1;
+        }
+        umma_conv::Params p = b.up;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out;
+        CK(b.umma->launch(b.map_a, b.map_b, p, b.grid, st));
+    }
+    if (b.pool_separate) {
+        simt::PoolParams q{};
+        q.in = conv_out; q.out = out; q.B = net->B; q.IH = b.ch; q.IW = b.cw; q.C = b.oc; q.OH = b.oh; q.OW = b.ow;
+        q.KH = q.KW = b.pool_k; q.SH = q.SW = b.pool_s; q.PT = b.ppt; q.PL = b.ppl;
+        CK(run_pool(q, b.out_bf16, net->num_sms, st));
+    }
+    return 0;
+}
+
+int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st) {
+    const void *cur = dev_in;
+    Block &first = net->blocks.front();
+    if (first.family != DNNB_KERNEL_SIMT) {
+        // a tcgen05 first block reads its storage type: TF32-rounded fp32, or bf16
+        const size_t n = (size_t)net->B * net->H * net->W * net->C;
+        const int grid = ew_grid(n, net->num_sms);
+        if (first.in_bf16)
+            simt::cast_input_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const float *)dev_in, (__nv_bfloat16 *)net->d_in_cast, n, 0);
+        else
+            simt::cast_input_kernel<float><<<grid, 256, 0, st>>>((const float *)dev_in, (float *)net->d_in_cast, n, 1);
+        CK(cudaGetLastError());
+        cur = net->d_in_cast;
+    }
+    for (size_t i = 0; i < net->blocks.size(); ++i) {
+        Block &b = net->blocks[i];
+        const bool last = i + 1 == net->blocks.size();
+        void *override_out = (last && dev_out && !b.out_bf16) ? dev_out : nullptr;
+        const bool prof = net->prof_block == (int)i && net->prof_used < 8192;
+        if (prof) {
+            if (net->prof_used == net->prof_events.size()) {
+                cudaEvent_t a, c;
+                CK(cudaEventCreate(&a));
+                CK(cudaEventCreate(&c));
+                net->prof_events.emplace_back(a, c);
+            }
+            CK(cudaEventRecord(net->prof_events[net->prof_used].first, st));
+        }
+        if (run_block(net, b, cur, override_out, st)) return 1;
+        if (prof) {
+            CK(cudaEventRecord(net->prof_events[net->prof_used].second, st));
+            net->prof_used++;
+        }
+        cur = override_out ? override_out : b.d_out;
+    }
+    return 0;
+}
+
+int check_net(dnnb_net *net, bool need_final) {
+    if (!net) return fail("null network handle");
+    if (need_final && !net->finalized) return fail("network not finalized");
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *dnnb_last_error(void) { return g_err.c_str(); }
+int dnnb_version(void) { return 100; }
+
+int dnnb_device_count(int *count) {
+    if (!count) return fail("null argument");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- op-level
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        CK(cudaMalloc(&p, bytes ? bytes : 4));
+        return 0;
+    }
+    float *f() { return static_cast<float *>(p); }
+};
+int sm_count() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+}  // namespace
+
+int conv2d_mul(float *in_layer, float *col, float *kernel_r, float *result, int batch, int oh, int ow, int od,
+               int ih, int iw, int ic, int kh, int kw, int sh, int sw) {
+    (void)col;
+    if (!in_layer || !kernel_r || !result) return fail("conv2d_mul: null pointer");
+    const size_t n_in = (size_t)batch * ih * iw * ic, n_out = (size_t)batch * oh * ow * od;
+    const size_t n_k = (size_t)kh * kw * ic * od;
+    // kernel_r[(c*kh*kw + di*kw + dj)][d]  ->  HWIO
+    std::vector<float> hwio(n_k);
+    for (int c = 0; c < ic; ++c)
+        for (int t = 0; t < kh * kw; ++t)
+            memcpy(&hwio[((size_t)t * ic + c) * od], &kernel_r[((size_t)c * kh * kw + t) * od], sizeof(float) * od);
+    DevBuf din, dk, dout;
+    if (din.alloc(n_in * 4) || dk.alloc(n_k * 4) || dout.alloc(n_out * 4)) return 1;
+    CK(cudaMemcpy(din.p, in_layer, n_in * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.p, hwio.data(), n_k * 4, cudaMemcpyHostToDevice));
+    simt::ConvParams p{};
+    p.in = din.p; p.w = dk.f(); p.out = dout.p;
+    p.B = batch; p.IH = ih; p.IW = iw; p.IC = ic; p.OH = oh; p.OW = ow; p.OC = od;
+    p.KH = kh; p.KW = kw; p.SH = sh; p.SW = sw;
+    p.tiles_y = (oh + 7) / 8; p.tiles_x = (ow + 7) / 8;
+    CK(launch_simt_conv<float, float>(p, nullptr));
+    CK(cudaMemcpy(result, dout.p, n_out * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bias_add(float *in_layer, float *biases, float *result, int shape_b, int shape_h, int shape_w, int shape_d) {
+    if (!in_layer || !biases || !result) return fail("bias_add: null pointer");
+    const size_t n = (size_t)shape_b * shape_h * shape_w * shape_d;
+    DevBuf din, db, dout;
+    if (din.alloc(n * 4) || db.alloc((size_t)shape_d * 4) || dout.alloc(n * 4)) return 1;
+    CK(cudaMemcpy(din.p, in_layer, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db.p, biases, (size_t)shape_d * 4, cudaMemcpyHostToDevice));
+    simt::bias_add_kernel<<<ew_grid(n, sm_count()), 256>>>(din.f(), db.f(), dout.f(), n, shape_d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(result, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int batch_norm(float *in_layer, float *mean, float *variance, float *gamma, float epsilon, float *result, int batch,
+               int oh, int ow, int od) {
+    if (!in_layer || !mean || !variance || !gamma || !result) return fail("batch_norm: null pointer");
+    const size_t n = (size_t)batch * oh * ow * od;
+    std::vector<float> sd(od);
+    for (int d = 0; d < od; ++d) sd[d] = (float)sqrt((double)(variance[d] + epsilon));   // dnn_openblas.c:48-50
+    DevBuf din, dm, ds, dg, dout;
+    if (din.alloc(n * 4) || dm.alloc((size_t)od * 4) || ds.alloc((size_t)od * 4) || dg.alloc((size_t)od * 4) ||
+        dout.alloc(n * 4))
+        return 1;
+    CK(cudaMemcpy(din.p, in_layer, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dm.p, mean, (size_t)od * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ds.p, sd.data(), (size_t)od * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dg.p, gamma, (size_t)od * 4, cudaMemcpyHostToDevice));
+    simt::batch_norm_kernel<<<ew_grid(n, sm_count()), 256>>>(din.f(), dm.f(), ds.f(), dg.f(), dout.f(), n, od);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(result, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int max_pool2d(float *in_layer, float *result, int batch, int oh, int ow, int od, int ih, int iw, int ic, int kh,
+               int kw, int sh, int sw) {
+    if (!in_layer || !result) return fail("max_pool2d: null pointer");
+    if (od != ic) return fail("max_pool2d: od != ic");
+    if ((oh - 1) * sh + kh > ih || (ow - 1) * sw + kw > iw) return fail("max_pool2d: window leaves the padded input");
+    const size_t n_in = (size_t)batch * ih * iw * ic, n_out = (size_t)batch * oh * ow * od;
+    DevBuf din, dout;
+    if (din.alloc(n_in * 4) || dout.alloc(n_out * 4)) return 1;
+    CK(cudaMemcpy(din.p, in_layer, n_in * 4, cudaMemcpyHostToDevice));
+    simt::PoolParams q{};
+    q.in = din.p; q.out = dout.p; q.B = batch; q.IH = ih; q.IW = iw; q.C = ic; q.OH = oh; q.OW = ow;
+    q.KH = kh; q.KW = kw; q.SH = sh; q.SW = sw;
+    CK(run_pool(q, false, sm_count(), nullptr));
+    CK(cudaMemcpy(result, dout.p, n_out * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int leaky_relu(float *in_layer, float *result, int batch, int oh, int ow, int od) {
+    if (!in_layer || !result) return fail("leaky_relu: null pointer");
+    const size_t n = (size_t)batch * oh * ow * od;
+    DevBuf din, dout;
+    if (din.alloc(n * 4) || dout.alloc(n * 4)) return 1;
+    CK(cudaMemcpy(din.p, in_layer, n * 4, cudaMemcpyHostToDevice));
+    simt::leaky_relu_kernel<<<ew_grid(n, sm_count()), 256>>>(din.f(), dout.f(), n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(result, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- network
+int dnnb_net_create(int device, int precision, int batch, int in_h, int in_w, int in_c, dnnb_net **out) {
+    if (!out) return fail("null out pointer");
+    if (precision != DNNB_TF32 && precision != DNNB_BF16 && precision != DNNB_FP32) return fail("bad precision %d", precision);
+    if (batch <= 0 || in_h <= 0 || in_w <= 0 || in_c <= 0) return fail("bad input shape");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("device %d not present (%d devices)", device, ndev);
+    DeviceGuard g(device);
+    int major = 0, sms = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) return fail("device %d is sm_%d0: this library is built for sm_100a only", device, major);
+    dnnb_net *net = new dnnb_net();
+    net->device = device; net->precision = precision;
+    net->B = batch; net->H = in_h; net->W = in_w; net->C = in_c;
+    net->num_sms = sms;
+    cudaError_t e = cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete net; return fail("cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    *out = net;
+    return 0;
+}
+
+int dnnb_net_add_block(dnnb_net *net, const float *kernel, int kh, int kw, int ic, int oc, int padding_same,
+                       const float *biases, const float *mean, const float *variance, const float *gamma,
+                       float epsilon, int leaky, int pool_k, int pool_s, int pool_same) {
+    if (check_net(net, false)) return 1;
+    if (net->finalized) return fail("network already finalized");
+    if (!kernel || kh <= 0 || kw <= 0 || ic <= 0 || oc <= 0) return fail("bad kernel");
+    const bool bn = mean || variance || gamma;
+    if (bn && !(mean && variance && gamma)) return fail("batch norm needs mean, variance and gamma");
+    if (pool_k < 0 || (pool_k > 0 && pool_s <= 0)) return fail("bad pool");
+    int in_c = net->blocks.empty() ? net->C : net->blocks.back().oc;
+    if (ic != in_c) return fail("block %zu: kernel has %d input channels, input has %d", net->blocks.size(), ic, in_c);
+    Block b;
+    b.kh = kh; b.kw = kw; b.ic = ic; b.oc = oc; b.same = padding_same ? 1 : 0;
+    b.has_bn = bn; b.leaky = leaky != 0;
+    b.pool_k = pool_k; b.pool_s = pool_s; b.pool_same = pool_same ? 1 : 0;
+    b.kernel.assign(kernel, kernel + (size_t)kh * kw * ic * oc);
+    b.scale.resize(oc); b.shift.resize(oc);
+    for (int d = 0; d < oc; ++d) {
+        // fold  ((x + bias - mean) / sqrt(var + eps)) * gamma   into   x * scale + shift
+        double sc = 1.0, sh = biases ? (double)biases[d] : 0.0;
+        if (bn) {
+            const float sd = (float)sqrt((double)(variance[d] + epsilon));   // dnn_openblas.c:48-50
+            sc = (double)gamma[d] / (double)sd;
+            sh = (sh - (double)mean[d]) * sc;
+        }
+        b.scale[d] = (float)sc;
+        b.shift[d] = (float)sh;
+    }
+    net->blocks.push_back(std::move(b));
+    return 0;
+}
+
+int dnnb_net_finalize(dnnb_net *net) {
+    if (check_net(net, false)) return 1;
+    if (net->finalized) return fail("network already finalized");
+    if (net->blocks.empty()) return fail("network has no blocks");
+    DeviceGuard g(net->device);
+    if (load_driver_fns()) return 1;
+    int h = net->H, w = net->W;
+    bool in_bf16 = false;
+    net->launches = 0;
+    for (size_t i = 0; i < net->blocks.size(); ++i) {
+        Block &b = net->blocks[i];
+        b.ih = h; b.iw = w;
+        int pb;
+        out_pads(h, b.kh, 1, b.same, &b.ch, &b.pt, &pb);
+        out_pads(w, b.kw, 1, b.same, &b.cw, &b.pl, &pb);
+        if (b.ch <= 0 || b.cw <= 0) return fail("block %zu: empty conv output", i);
+        b.oh = b.ch; b.ow = b.cw;
+        if (b.pool_k > 0) {
+            out_pads(b.ch, b.pool_k, b.pool_s, b.pool_same, &b.oh, &b.ppt, &pb);
+            out_pads(b.cw, b.pool_k, b.pool_s, b.pool_same, &b.ow, &b.ppl, &pb);
+            if (b.oh <= 0 || b.ow <= 0) return fail("block %zu: empty pool output", i);
+        }
+        if (i == 0 && net->precision == DNNB_BF16) {
+            // would the first block run on tcgen05?  then its input is cast to bf16 first
+            plan_block(net, i, true);
+            if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
+        } else {
+            plan_block(net, i, in_bf16);
+        }
+        const size_t es_out = b.out_bf16 ? 2 : 4;
+        b.out_elems = (size_t)net->B * b.oh * b.ow * b.oc;
+        b.conv_out_elems = b.pool_fused ? b.out_elems : (size_t)net->B * b.ch * b.cw * b.oc;
+        CK(cudaMalloc(&b.d_out, b.out_elems * es_out));
+        if (b.pool_separate) CK(cudaMalloc(&b.d_conv_out, b.conv_out_elems * es_out));
+        else b.d_conv_out = b.d_out;
+        // epilogue constants, padded to the N tiling
+        const int ocp = b.family == DNNB_KERNEL_SIMT ? b.oc : b.up.num_n_tiles * b.bn;
+        std::vector<float> sc(ocp, 0.f), sh(ocp, 0.f);
+        memcpy(sc.data(), b.scale.data(), sizeof(float) * b.oc);
+        memcpy(sh.data(), b.shift.data(), sizeof(float) * b.oc);
+        CK(cudaMalloc(&b.d_scale, sizeof(float) * ocp));
+        CK(cudaMalloc(&b.d_shift, sizeof(float) * ocp));
+        CK(cudaMemcpy(b.d_scale, sc.data(), sizeof(float) * ocp, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(b.d_shift, sh.data(), sizeof(float) * ocp, cudaMemcpyHostToDevice));
+        if (b.family == DNNB_KERNEL_SIMT) {
+            CK(cudaMalloc(&b.d_kernel, sizeof(float) * b.kernel.size()));
+            CK(cudaMemcpy(b.d_kernel, b.kernel.data(), sizeof(float) * b.kernel.size(), cudaMemcpyHostToDevice));
+        } else {
+            // prepack HWIO -> [tap][OCp][IC], K-major, rounded once to the MMA operand type
+            const int taps = b.kh * b.kw;
+            const size_t n = (size_t)taps * ocp * b.ic;
+            if (b.in_bf16) {
+                std::vector<uint16_t> pk(n, 0);
+                for (int t = 0; t < taps; ++t)
+                    for (int c = 0; c < b.ic; ++c)
+                        for (int d = 0; d < b.oc; ++d)
+                            pk[((size_t)t * ocp + d) * b.ic + c] = host_bf16(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
+                CK(cudaMalloc(&b.d_wpack, n * 2));
+                CK(cudaMemcpy(b.d_wpack, pk.data(), n * 2, cudaMemcpyHostToDevice));
+            } else {
+                std::vector<float> pk(n, 0.f);
+                for (int t = 0; t < taps; ++t)
+                    for (int c = 0; c < b.ic; ++c)
+                        for (int d = 0; d < b.oc; ++d)
+                            pk[((size_t)t * ocp + d) * b.ic + c] = host_round_tf32(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
+                CK(cudaMalloc(&b.d_wpack, n * 4));
+                CK(cudaMemcpy(b.d_wpack, pk.data(), n * 4, cudaMemcpyHostToDevice));
+            }
+            if (encode_map_b(b)) return 1;
+        }
+        net->launches += 1 + (b.pool_separate ? 1 : 0);
+        in_bf16 = b.out_bf16;
+        h = b.oh; w = b.ow;
+    }
+    const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
+    CK(cudaMalloc(&net->d_in, n_in * 4));
+    Block &first = net->blocks.front();
+    if (first.family != DNNB_KERNEL_SIMT) {
+        CK(cudaMalloc(&net->d_in_cast, n_in * (first.in_bf16 ? 2 : 4)));
+        net->launches += 1;
+        if (encode_map_a(net, first, net->d_in_cast)) return 1;
+    }
+    for (size_t i = 1; i < net->blocks.size(); ++i)
+        if (net->blocks[i].family != DNNB_KERNEL_SIMT)
+            if (encode_map_a(net, net->blocks[i], net->blocks[i - 1].d_out)) return 1;
+    Block &lastb = net->blocks.back();
+    if (lastb.out_bf16) return fail("internal: last block stored as bf16");
+    net->finalized = true;
+    return 0;
+}
+
+int dnnb_net_num_blocks(dnnb_net *net, int *n) {
+    if (check_net(net, false) || !n) return fail("bad argument");
+    *n = (int)net->blocks.size();
+    return 0;
+}
+
+int dnnb_net_out_shape(dnnb_net *net, int *b, int *h, int *w, int *c) {
+    if (check_net(net, true)) return 1;
+    const Block &l = net->blocks.back();
+    if (b) *b = net->B;
+    if (h) *h = l.oh;
+    if (w) *w = l.ow;
+    if (c) *c = l.oc;
+    return 0;
+}
+
+int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, void *stream) {
+    if (check_net(net, true)) return 1;
+    if (!dev_in) return fail("null device input");
+    DeviceGuard g(net->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
+    return forward_impl(net, dev_in, dev_out, st);
+}
+
+int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out) {
+    if (check_net(net, true)) return 1;
+    if (!host_in || !host_out) return fail("null host buffer");
+    DeviceGuard g(net->device);
+    const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
+    CK(cudaMemcpyAsync(net->d_in, host_in, n_in * 4, cudaMemcpyHostToDevice, net->stream));
+    if (forward_impl(net, net->d_in, nullptr, net->stream)) return 1;
+    const Block &l = net->blocks.back();
+    CK(cudaMemcpyAsync(host_out, l.d_out, l.out_elems * 4, cudaMemcpyDeviceToHost, net->stream));
+    return 0;
+}
+
+int dnnb_net_sync(dnnb_net *net) {
+    if (check_net(net, false)) return 1;
+    DeviceGuard g(net->device);
+    CK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+int dnnb_net_forward(dnnb_net *net, const float *host_in, float *host_out) {
+    if (dnnb_net_forward_async(net, host_in, host_out)) return 1;
+    return dnnb_net_sync(net);
+}
+
+int dnnb_net_block_output(dnnb_net *net, int block, float *host_out) {
+    if (check_net(net, true)) return 1;
+    if (block < 0 || block >= (int)net->blocks.size() || !host_out) return fail("bad block index or buffer");
+    DeviceGuard g(net->device);
+    Block &b = net->blocks[block];
+    CK(cudaStreamSynchronize(net->stream));
+    if (!b.out_bf16) {
+        CK(cudaMemcpy(host_out, b.d_out, b.out_elems * 4, cudaMemcpyDeviceToHost));
+    } else {
+        DevBuf tmp;
+        if (tmp.alloc(b.out_elems * 4)) return 1;
+        simt::cast_output_kernel<__nv_bfloat16><<<ew_grid(b.out_elems, net->num_sms), 256>>>(
+            (const __nv_bfloat16 *)b.d_out, tmp.f(), b.out_elems);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(host_out, tmp.p, b.out_elems * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
+    if (check_net(net, true)) return 1;
+    if (block < 0 || block >= (int)net->blocks.size() || !info) return fail("bad block index or buffer");
+    const Block &b = net->blocks[block];
+    info[0] = b.family; info[1] = b.oh; info[2] = b.ow; info[3] = b.oc;
+    info[4] = b.pool_fused ? 1 : 0;
+    info[5] = b.bn; info[6] = b.swz; info[7] = b.umma ? b.umma->stages : 0; info[8] = b.grid;
+    info[9] = b.pool_separate ? 1 : 0;
+    info[10] = b.out_bf16 ? 2 : 4;
+    info[11] = 1 + (b.pool_separate ? 1 : 0);
+    return 0;
+}
+
+int dnnb_net_time_blocks(dnnb_net *net, int warmup, int iters, float *ms) {
+    if (check_net(net, true)) return 1;
+    if (!ms || iters <= 0 || warmup < 0) return fail("bad argument");
+    DeviceGuard g(net->device);
+    const size_t flush_bytes = 256u << 20;   // > 126 MB L2
+    if (!net->d_flush) CK(cudaMalloc(&net->d_flush, flush_bytes));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    cudaStream_t st = net->stream;
+    // one full forward first so every block has a real input
+    if (forward_impl(net, net->d_in, nullptr, st)) return 1;
+    const void *cur = net->blocks.front().family != DNNB_KERNEL_SIMT ? net->d_in_cast : (const void *)net->d_in;
+    for (size_t i = 0; i < net->blocks.size(); ++i) {
+        Block &b = net->blocks[i];
+        double total = 0.0;
+        for (int it = 0; it < warmup + iters; ++it) {
+            CK(cudaMemsetAsync(net->d_flush, it & 0xff, flush_bytes, st));
+            CK(cudaEventRecord(e0, st));
+            if (run_block(net, b, cur, nullptr, st)) return 1;
+            CK(cudaEventRecord(e1, st));
+            CK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (it >= warmup) total += t;
+        }
+        ms[i] = (float)(total / iters);
+        cur = b.d_out;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+int dnnb_net_profile_block(dnnb_net *net, int block) {
+    if (check_net(net, true)) return 1;
+    if (block >= (int)net->blocks.size()) return fail("bad block index");
+    net->prof_block = block;   // < 0 switches profiling off
+    net->prof_used = 0;
+    return 0;
+}
+
+int dnnb_net_profile_read(dnnb_net *net, float *total_ms, int *count) {
+    if (check_net(net, true) || !total_ms || !count) return fail("bad argument");
+    DeviceGuard g(net->device);
+    double total = 0.0;
+    for (size_t i = 0; i < net->prof_used; ++i) {
+        CK(cudaEventSynchronize(net->prof_events[i].second));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, net->prof_events[i].first, net->prof_events[i].second));
+        total += t;
+    }
+    *total_ms = (float)total;
+    *count = (int)net->prof_used;
+    net->prof_used = 0;
+    return 0;
+}
+
+int dnnb_net_launches_per_forward(dnnb_net *net, int *n) {
+    if (check_net(net, true) || !n) return fail("bad argument");
+    *n = net->launches;
+    return 0;
+}
+
+int dnnb_net_destroy(dnnb_net *net) {
+    if (!net) return 0;
+    DeviceGuard g(net->device);
+    if (net->stream) cudaStreamSynchronize(net->stream);
+    for (Block &b : net->blocks) {
+        if (b.pool_separate && b.d_conv_out) cudaFree(b.d_conv_out);
+        if (b.d_out) cudaFree(b.d_out);
+        if (b.d_kernel) cudaFree(b.d_kernel);
+        if (b.d_wpack) cudaFree(b.d_wpack);
+        if (b.d_scale) cudaFree(b.d_scale);
+        if (b.d_shift) cudaFree(b.d_shift);
+    }
+    for (auto &pr : net->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    if (net->d_in) cudaFree(net->d_in);
+    if (net->d_in_cast) cudaFree(net->d_in_cast);
+    if (net->d_out_f32) cudaFree(net->d_out_f32);
+    if (net->d_flush) cudaFree(net->d_flush);
+    if (net->stream) cudaStreamDestroy(net->stream);
+    delete net;
+    return 0;
+}
+
+// pinned host buffers for the end-to-end path (async H2D / D2H need page-locked memory)
+int dnnb_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail("null out pointer");
+    CK(cudaHostAlloc(out, bytes ? bytes : 4, cudaHostAllocPortable));
+    return 0;
+}
+int dnnb_host_free(void *p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+int dnnb_measure_mma_peak(int device, int precision, float *tflops) {
+    if (!tflops) return fail("null argument");
+    if (precision != DNNB_TF32 && precision != DNNB_BF16) return fail("precision must be TF32 or BF16");
+    DeviceGuard g(device);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int smem = 128 * 128 + 256 * 128 + 1024;
+    const int iters = 4096;
+    auto run = [&](int n) -> cudaError_t {
+        if (precision == DNNB_BF16) {
+            cudaFuncSetAttribute(umma_conv::mma_peak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            umma_conv::mma_peak_kernel<true><<<sms, 64, smem>>>(n);
+        } else {
+            cudaFuncSetAttribute(umma_conv::mma_peak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            umma_conv::mma_peak_kernel<false><<<sms, 64, smem>>>(n);
+        }
+        return cudaGetLastError();
+    };
+    CK(run(256));
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        CK(run(iters));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        if (t < best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double k_per_mma = precision == DNNB_BF16 ? 16.0 : 8.0;
+    const double flops = (double)sms * iters * 4.0 * 2.0 * 128.0 * 256.0 * k_per_mma;
+    *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    return 0;
+}
+
+}  // extern "C"

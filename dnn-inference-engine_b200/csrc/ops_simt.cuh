@@ -1,0 +1,215 @@
+// ops_simt.cuh -- CUDA-core kernels: the generic fused direct convolution (any shape; used for
+// layer 0 whose 3 input channels do not meet TMA's 16-byte rule, for shapes the tcgen05
+// kernel does not cover, for DNNB_FP32, and by the op-level conv2d_mul entry point), the
+// generic NHWC max-pool, and the three element-wise ops of the op-level API.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace simt {
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+struct ConvParams {
+    const void *in;      // [B, IH, IW, IC]
+    const float *w;      // HWIO [KH, KW, IC, OC] fp32
+    void *out;           // [B, OH', OW', OC]  (OH' = OH/2 when pool)
+    const float *scale;  // [OC] or nullptr (=1)
+    const float *shift;  // [OC] or nullptr (=0)
+    int B, IH, IW, IC;
+    int OH, OW, OC;      // conv output (before any fused pool)
+    int KH, KW, SH, SW, PT, PL;
+    int leaky;           // LeakyReLU(0.1) after scale/shift
+    int pool;            // fused 2x2 stride-2 max-pool (OH, OW even)
+    int round_tf32;      // round stored fp32 values to TF32 (feeds a kind::tf32 block)
+    int tiles_y, tiles_x;
+};
+
+// Implicit-GEMM direct convolution on CUDA cores.  One block = an 8x8 patch of output pixels
+// of one image x 64 output channels; 256 threads; thread (ty, tx) owns the 2x2 pixel window
+// ty (so a fused 2x2/2 pool is thread-local) x 4 consecutive channels tx*4.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) conv_fused_kernel(const ConvParams p) {
+    constexpr int KC = 16;
+    __shared__ __align__(16) float As[KC][64];  // [c][pixel slot], slot = window*4 + (i*2+j)
+    __shared__ __align__(16) float Bs[KC][64];  // [c][oc]
+
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    int t = blockIdx.x;
+    const int tile_x = t % p.tiles_x; t /= p.tiles_x;
+    const int tile_y = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int oc0 = blockIdx.y * 64;
+    const TIn *in = static_cast<const TIn *>(p.in) + (size_t)b * p.IH * p.IW * p.IC;
+
+    // A-load role: slot = tid / 4, channels (tid % 4) * 4 .. +3
+    const int a_slot = tid >> 2, a_c = (tid & 3) * 4;
+    const int a_win = a_slot >> 2, a_sub = a_slot & 3;
+    const int a_oy = tile_y * 8 + (a_win >> 2) * 2 + (a_sub >> 1);
+    const int a_ox = tile_x * 8 + (a_win & 3) * 2 + (a_sub & 1);
+    // B-load role: row tid / 16, cols (tid % 16) * 4 .. +3
+    const int b_row = tid >> 4, b_col = (tid & 15) * 4;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int di = 0; di < p.KH; ++di) {
+        for (int dj = 0; dj < p.KW; ++dj) {
+            const int iy = a_oy * p.SH + di - p.PT;
+            const int ix = a_ox * p.SW + dj - p.PL;
+            const bool a_ok = a_oy < p.OH && a_ox < p.OW && iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW;
+            const TIn *a_src = in + ((size_t)iy * p.IW + ix) * p.IC;
+            const float *w_tap = p.w + (size_t)(di * p.KW + dj) * p.IC * p.OC;
+            for (int c0 = 0; c0 < p.IC; c0 += KC) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + a_c + k;
+                    As[a_c + k][a_slot] = (a_ok && c < p.IC) ? to_f32<TIn>(a_src[c]) : 0.f;
+                }
+                {
+                    const int c = c0 + b_row;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int oc = oc0 + b_col + k;
+                        Bs[b_row][b_col + k] = (c < p.IC && oc < p.OC) ? w_tap[(size_t)c * p.OC + oc] : 0.f;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const float4 a = *reinterpret_cast<const float4 *>(&As[c][ty * 4]);
+                    const float4 w = *reinterpret_cast<const float4 *>(&Bs[c][tx * 4]);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+                }
+                __syncthreads();
+            }
+        }
+    }
+
+    // epilogue: scale/shift -> leaky -> (round) -> (pool) -> store
+    const int wy = ty >> 2, wx = ty & 3;
+    TOut *out = static_cast<TOut *>(p.out);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int oc = oc0 + tx * 4 + j;
+        if (oc >= p.OC) continue;
+        const float sc = p.scale ? p.scale[oc] : 1.f;
+        const float sh = p.shift ? p.shift[oc] : 0.f;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float y = p.scale || p.shift ? fmaf(acc[i][j], sc, sh) : acc[i][j];
+            if (p.leaky) y = y < 0.f ? 0.1f * y : y;
+            if (p.round_tf32) y = ptx::round_tf32(y);
+            v[i] = y;
+        }
+        if (p.pool) {
+            const int py = tile_y * 4 + wy, px = tile_x * 4 + wx;
+            if (py < p.OH / 2 && px < p.OW / 2) {
+                float m = v[0];
+#pragma unroll
+                for (int i = 1; i < 4; ++i) m = m >= v[i] ? m : v[i];
+                out[(((size_t)b * (p.OH / 2) + py) * (p.OW / 2) + px) * p.OC + oc] = from_f32<TOut>(m);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int oy = tile_y * 8 + wy * 2 + (i >> 1), ox = tile_x * 8 + wx * 2 + (i & 1);
+                if (oy < p.OH && ox < p.OW)
+                    out[(((size_t)b * p.OH + oy) * p.OW + ox) * p.OC + oc] = from_f32<TOut>(v[i]);
+            }
+        }
+    }
+}
+
+struct PoolParams {
+    const void *in;  // [B, IH, IW, C]
+    void *out;       // [B, OH, OW, C]
+    int B, IH, IW, C, OH, OW;
+    int KH, KW, SH, SW, PT, PL;
+};
+
+// Generic NHWC max-pool; positions outside the input count as finfo(float32).min, which is what
+// the reference's host layer pads with (proj3/dnn_openblas.py:232-235).  One thread per output
+// element, channel fastest.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolParams p) {
+    const size_t total = (size_t)p.B * p.OH * p.OW * p.C;
+    const T *in = static_cast<const T *>(p.in);
+    T *out = static_cast<T *>(p.out);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % p.C;
+        size_t r = idx / p.C;
+        const int ox = r % p.OW; r /= p.OW;
+        const int oy = r % p.OH;
+        const int b = r / p.OH;
+        float m = -FLT_MAX;
+        bool first = true;
+        for (int di = 0; di < p.KH; ++di)
+            for (int dj = 0; dj < p.KW; ++dj) {
+                const int iy = oy * p.SH + di - p.PT, ix = ox * p.SW + dj - p.PL;
+                float v = -FLT_MAX;
+                if (iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW)
+                    v = to_f32<T>(in[(((size_t)b * p.IH + iy) * p.IW + ix) * p.C + c]);
+                if (first) { m = v; first = false; }
+                else m = m >= v ? m : v;   // MAX macro of proj3/dnn_openblas.c:7
+            }
+        out[idx] = from_f32<T>(m);
+    }
+}
+
+// ---- op-level element-wise kernels (bit-exact restatements of proj3/dnn_openblas.c) ----------
+__global__ void bias_add_kernel(const float *in, const float *bias, float *out, size_t n, int d) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[i] + bias[i % d];
+}
+// sd[d] = (float)sqrt((double)(var[d] + eps)) is computed on the host exactly as :48-50 does
+__global__ void batch_norm_kernel(const float *in, const float *mean, const float *sd, const float *gamma,
+                                  float *out, size_t n, int d) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % d;
+        out[i] = __fmul_rn(__fdiv_rn(__fsub_rn(in[i], mean[c]), sd[c]), gamma[c]);
+    }
+}
+__global__ void leaky_relu_kernel(const float *in, float *out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float t = in[i];
+        out[i] = t < 0 ? (float)(0.1 * (double)t) : t;   // double literal, :249
+    }
+}
+
+// fp32 -> activation dtype of the first tcgen05 block (TF32-rounded fp32, or bf16)
+template <typename TOut>
+__global__ void cast_input_kernel(const float *in, TOut *out, size_t n, int round_tf32) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = in[i];
+        if (round_tf32) v = ptx::round_tf32(v);
+        out[i] = from_f32<TOut>(v);
+    }
+}
+template <typename TIn>
+__global__ void cast_output_kernel(const TIn *in, float *out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = to_f32<TIn>(in[i]);
+}
+
+}  // namespace simt

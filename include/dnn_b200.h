@@ -1,0 +1,149 @@
+/* dnn_b200.h -- C ABI of libdnn_b200.so, the sm_100a replacement for the native op
+ * libraries of tink-expo/dnn-inference-engine proj3 (libdnn_openblas.so / libdnn_avx.so /
+ * libdnn_cublas.so / libdnn_cuda.so, proj3/Makefile:1-15).
+ *
+ * Two groups of entry points:
+ *
+ *  1. Op-level functions with the names and argument lists of proj3/dnn_openblas.c, taking
+ *     HOST pointers.  proj3/dnn_openblas.py binds them unchanged
+ *     (ctypes.cdll.LoadLibrary, proj3/dnn_openblas.py:9); each call uploads, runs one CUDA
+ *     kernel and downloads.  They exist for op-by-op parity and for the debug
+ *     (layer_N.npy) mode of the host engine; they are not the fast path.
+ *
+ *  2. A resident network API (dnnb_net_*): weights are uploaded and prepacked once,
+ *     activations stay in HBM across all conv blocks, and one forward call runs the whole
+ *     fused chain.  This is what dnn_b200.DnnInferenceEngine.run uses.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure, and
+ * dnnb_last_error() then describes the failure (the reference has no error convention at all:
+ * void returns, unchecked CUDA statuses -- SURVEY.md 8b).  All tensors are NHWC float32 on
+ * the host side.  Host buffers stay owned by the caller and are not retained after a call.
+ * Inputs are never written (the reference's batch_norm overwrites its variance argument,
+ * proj3/dnn_openblas.c:48-50; this library does not).  There is no CPU fallback: without a
+ * CUDA device every compute entry point fails.
+ */
+#ifndef DNN_B200_H
+#define DNN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dnnb_net dnnb_net; /* opaque network handle */
+
+/* arithmetic the conv blocks run in */
+#define DNNB_TF32 0 /* tcgen05 kind::tf32, fp32 activations rounded to TF32 (RN) between blocks */
+#define DNNB_BF16 1 /* tcgen05 kind::f16 (bf16 operands), bf16 activations between blocks        */
+#define DNNB_FP32 2 /* CUDA-core fp32 kernels only (debug / tight-parity path)                    */
+
+/* kernel family chosen for a block, reported by dnnb_net_block_info */
+#define DNNB_KERNEL_SIMT 0      /* CUDA-core direct convolution                 */
+#define DNNB_KERNEL_UMMA_TILED 1 /* tcgen05 implicit GEMM, TMA tiled boxes, fused 2x2/2 pool */
+#define DNNB_KERNEL_UMMA_IM2COL 2 /* tcgen05 implicit GEMM, TMA im2col loads     */
+
+const char *dnnb_last_error(void);
+int dnnb_version(void);
+int dnnb_device_count(int *count);
+
+/* ---- 1. op-level, reference signatures (host pointers) --------------------------------- */
+
+/* proj3/dnn_openblas.c:160-194.  in_layer is the zero-padded input [batch,ih,iw,ic]; col is
+ * the reference's im2col scratch and is ignored; kernel_r is [ic*kh*kw, od] with
+ * k = c*kh*kw + di*kw + dj (proj3/dnn_openblas.py:166-167).  Unlike the reference (:170)
+ * batch > 1 is handled correctly. */
+int conv2d_mul(float *in_layer, float *col, float *kernel_r, float *result,
+               int batch, int oh, int ow, int od, int ih, int iw, int ic,
+               int kh, int kw, int sh, int sw);
+/* proj3/dnn_openblas.c:9-38 */
+int bias_add(float *in_layer, float *biases, float *result,
+             int shape_b, int shape_h, int shape_w, int shape_d);
+/* proj3/dnn_openblas.c:40-65; variance is NOT modified; batch > 1 handled */
+int batch_norm(float *in_layer, float *mean, float *variance, float *gamma, float epsilon,
+               float *result, int batch, int oh, int ow, int od);
+/* proj3/dnn_openblas.c:196-234; in_layer is padded with finfo(float32).min by the caller
+ * (proj3/dnn_openblas.py:232-235).  The reference's host passes four trailing pad ints that
+ * its C ignores (proj3/dnn_openblas.py:242); they are accepted and ignored here too. */
+int max_pool2d(float *in_layer, float *result,
+               int batch, int oh, int ow, int od, int ih, int iw, int ic,
+               int kh, int kw, int sh, int sw);
+/* proj3/dnn_openblas.c:236-254 */
+int leaky_relu(float *in_layer, float *result, int batch, int oh, int ow, int od);
+
+/* ---- 2. resident network API ----------------------------------------------------------- */
+
+/* Creates an empty network on `device` for inputs [batch,in_h,in_w,in_c] float32 NHWC. */
+int dnnb_net_create(int device, int precision, int batch, int in_h, int in_w, int in_c,
+                    dnnb_net **out);
+
+/* Appends one fused block  Conv2D -> [+bias] -> [BatchNorm] -> [LeakyReLU(0.1)] -> [MaxPool2D],
+ * i.e. the node run of proj3/yolov2tiny.py:30-34.  kernel is HWIO [kh,kw,ic,oc]; stride 1.
+ * biases may be NULL; mean/variance/gamma NULL => no batch norm; pool_k == 0 => no pool.
+ * padding_same / pool_same: 1 = 'SAME', 0 = 'VALID' (proj3/dnn_openblas.py:127-142).
+ * All arrays are copied; none is modified. */
+int dnnb_net_add_block(dnnb_net *net, const float *kernel, int kh, int kw, int ic, int oc,
+                       int padding_same, const float *biases,
+                       const float *mean, const float *variance, const float *gamma, float epsilon,
+                       int leaky, int pool_k, int pool_s, int pool_same);
+
+/* Chooses a kernel per block, prepacks weights, allocates the HBM-resident activations. */
+int dnnb_net_finalize(dnnb_net *net);
+
+int dnnb_net_num_blocks(dnnb_net *net, int *n);
+int dnnb_net_out_shape(dnnb_net *net, int *b, int *h, int *w, int *c);
+
+/* Host in / host out: H2D copy, all blocks, D2H copy; returns when host_out is valid. */
+int dnnb_net_forward(dnnb_net *net, const float *host_in, float *host_out);
+
+/* Device in / device out (float32 NHWC in HBM), asynchronous on `stream` (a cudaStream_t, or
+ * NULL for the network's own stream).  dev_out may be NULL: the result then stays in the
+ * network's last activation buffer (see dnnb_net_block_output_ptr). */
+int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, void *stream);
+
+/* As dnnb_net_forward but only enqueues (H2D, blocks, D2H) on the network's own stream and
+ * returns; host_in / host_out should be page-locked (dnnb_host_alloc) and must stay valid until
+ * dnnb_net_sync returns.  Lets one host thread keep several devices busy. */
+int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out);
+
+/* Waits for everything queued on the network's own stream. */
+int dnnb_net_sync(dnnb_net *net);
+
+/* Debug / layer-wise comparison: copies block `block`'s output (after its pool, if any) to
+ * host as float32 [b,h,w,c]; shape via dnnb_net_block_info. */
+int dnnb_net_block_output(dnnb_net *net, int block, float *host_out);
+
+/* info[0..11] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
+ * epilogue), BN tile, swizzle bytes, stages, grid, separate-pool-kernel(0/1), elem bytes of the
+ * stored activation, launches per forward} */
+int dnnb_net_block_info(dnnb_net *net, int block, int *info);
+
+/* Times each block's kernels with CUDA events on the network's stream: `iters` timed
+ * repetitions after `warmup`; ms[block] = mean milliseconds per forward of that block. */
+int dnnb_net_time_blocks(dnnb_net *net, int warmup, int iters, float *ms);
+
+/* In-situ timing of one block inside real forwards: after dnnb_net_profile_block(net, b) every
+ * forward records a CUDA-event pair around block b's kernels on the stream it runs on;
+ * dnnb_net_profile_read waits for them, returns their summed duration and count, and resets.
+ * block < 0 switches it off. */
+int dnnb_net_profile_block(dnnb_net *net, int block);
+int dnnb_net_profile_read(dnnb_net *net, float *total_ms, int *count);
+
+/* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
+int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
+
+int dnnb_net_destroy(dnnb_net *net);
+
+/* Page-locked host memory for the end-to-end path. */
+int dnnb_host_alloc(size_t bytes, void **out);
+int dnnb_host_free(void *p);
+
+/* Measures dense tcgen05 throughput (TFLOP/s) of kind::tf32 (precision 0) or kind::f16 bf16
+ * (precision 1) with a register-free MMA issue loop on every SM: the tensor-pipe roofline
+ * denominator for TF32, which MEASURED_PEAKS.json does not hold. */
+int dnnb_measure_mma_peak(int device, int precision, float *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

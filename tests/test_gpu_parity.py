@@ -1,0 +1,304 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libdnn_b200.so via ctypes) and is checked against the CPU oracle (oracle/) on the same seeded
+inputs, and against the committed golden vectors the reference itself produced.
+
+Tolerances (BASELINE.json north_star): normalised error max|out-ref|/max|ref| <= 1e-2 for TF32,
+<= 3e-2 for BF16 on the [13,13,125] output; op-level fp32 entry points are bit-exact except the
+convolution (summation order), which is held to 1e-5.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, normalised_error
+import _lib
+import chain
+import dnn_b200
+from synth import CHANNELS, KSIZES, POOLS, build_yolov2tiny, make_images, make_weights
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32": 1e-2, "bf16": 3e-2, "fp32": 1e-4}
+OPS = np.load(os.path.join(GOLDEN, "ops_small.npz"))
+
+
+def _single(x, fn, debug=True):
+    g = dnn_b200.DnnGraphBuilder()
+    i = g.create_input(list(x.shape))
+    g.set_out_node(fn(g, i))
+    return dnn_b200.DnnInferenceEngine(g, debug).run(x)
+
+
+# ------------------------------------------------------------------------------- op level
+def test_op_level_entry_points_against_reference_goldens(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    o = OPS
+    for name, pad in [("conv3_same", 'SAME'), ("conv3_valid", 'VALID')]:
+        y = _single(o[name + "_x"], lambda g, i: g.create_conv2d(i, o["conv3_k"], [1, 1, 1, 1], pad))
+        np.testing.assert_allclose(y, o[name + "_y"], rtol=1e-5, atol=1e-5)
+    y = _single(o["conv1_same_x"], lambda g, i: g.create_conv2d(i, o["conv1_k"], [1, 1, 1, 1], 'SAME'))
+    np.testing.assert_allclose(y, o["conv1_same_y"], rtol=1e-5, atol=1e-5)
+    y = _single(o["bias_x"], lambda g, i: g.create_bias_add(i, o["bias_b"]))
+    np.testing.assert_array_equal(y, o["bias_y"])
+    y = _single(o["bn_x"], lambda g, i: g.create_batch_norm(i, o["bn_mean"], o["bn_var"], o["bn_gamma"], 1e-5))
+    np.testing.assert_array_equal(y, o["bn_y"])
+    y = _single(o["leaky_x"], lambda g, i: g.create_leaky_relu(i))
+    np.testing.assert_array_equal(y, o["leaky_y"])
+    for name, s in [("pool_s2_even", 2), ("pool_s2_odd", 2), ("pool_s1_same", 1), ("pool_ties", 2)]:
+        y = _single(o[name + "_x"], lambda g, i: g.create_max_pool2d(i, [1, 2, 2, 1], [1, s, s, 1], 'SAME'))
+        np.testing.assert_array_equal(y, o[name + "_y"])
+    assert sorted(os.listdir(tmp_path / "intermediate"))[0] == "layer_0.npy"   # debug dump convention
+
+
+def test_op_level_bit_exact_on_larger_random_tensors(oracle_libs):
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal((3, 26, 26, 40)) * 3).astype(np.float32)
+    b = rng.standard_normal(40).astype(np.float32)
+    mean, var = rng.standard_normal(40).astype(np.float32), rng.uniform(0.1, 2, 40).astype(np.float32)
+    gamma = rng.uniform(-2, 2, 40).astype(np.float32)
+    var_before = var.copy()
+
+    def both(fn):
+        c = chain.Chain("oracle"); fn(c, c.create_input(x.shape))
+        return _single(x, fn, debug=True), c.run(x)
+
+    for fn in (lambda g, i: g.create_bias_add(i, b),
+               lambda g, i: g.create_batch_norm(i, mean, var, gamma, 1e-5),
+               lambda g, i: g.create_leaky_relu(i),
+               lambda g, i: g.create_max_pool2d(i, [1, 2, 2, 1], [1, 2, 2, 1], 'SAME'),
+               lambda g, i: g.create_max_pool2d(i, [1, 2, 2, 1], [1, 1, 1, 1], 'SAME'),
+               lambda g, i: g.create_max_pool2d(i, [1, 3, 3, 1], [1, 2, 2, 1], 'VALID')):
+        got, ref = both(fn)
+        np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(var, var_before)        # unlike the reference, inputs are not written
+    k = rng.standard_normal((3, 3, 40, 24)).astype(np.float32)
+    got, ref = both(lambda g, i: g.create_conv2d(i, k, [1, 1, 1, 1], 'SAME'))
+    assert normalised_error(got, ref) < 1e-5
+    got, ref = both(lambda g, i: g.create_conv2d(i, k, [1, 2, 2, 1], 'SAME'))     # strided, the op-level ABI allows it
+    assert got.shape == (3, 13, 13, 24) and normalised_error(got, ref) < 1e-5
+
+
+def test_library_can_be_bound_the_way_the_reference_binds_it(oracle_libs):
+    """proj3/dnn_openblas.py:9,180-188,236-242 style: cdll.LoadLibrary, no argtypes/restype, every
+    int wrapped in c_int, four extra pad ints on max_pool2d."""
+    mylib = ctypes.cdll.LoadLibrary(_lib.LIB_PATH)
+    fpt = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 9, 9, 6)).astype(np.float32)
+    k = rng.standard_normal((3, 3, 6, 10)).astype(np.float32)
+    xp = np.pad(x, [(0, 0), (1, 1), (1, 1), (0, 0)], 'constant')
+    kernel_r = np.ascontiguousarray(k.transpose(2, 0, 1, 3).reshape(-1, 10))
+    col = np.zeros((2, 81, 54), np.float32)
+    res = np.zeros((2, 9, 9, 10), np.float32)
+    mylib.conv2d_mul(xp.ctypes.data_as(fpt), col.ctypes.data_as(fpt), kernel_r.ctypes.data_as(fpt),
+                     res.ctypes.data_as(fpt), *map(ctypes.c_int, res.shape), *map(ctypes.c_int, xp.shape[1:]),
+                     *map(ctypes.c_int, k.shape[:2]), *map(ctypes.c_int, [1, 1]))
+    c = chain.Chain("oracle"); c.create_conv2d(c.create_input(x.shape), k, [1, 1, 1, 1], 'SAME')
+    assert normalised_error(res, c.run(x)) < 1e-5
+    pp = np.pad(res, [(0, 0), (0, 1), (0, 1), (0, 0)], 'constant', constant_values=np.finfo('float32').min)
+    pooled = np.zeros((2, 9, 9, 10), np.float32)
+    mylib.max_pool2d(pp.ctypes.data_as(fpt), pooled.ctypes.data_as(fpt), *pooled.shape, *pp.shape[1:], 2, 2, 1, 1, 0, 1, 0, 1)
+    c = chain.Chain("oracle"); c.create_max_pool2d(c.create_input(res.shape), [1, 2, 2, 1], [1, 1, 1, 1], 'SAME')
+    np.testing.assert_array_equal(pooled, c.run(res))
+
+
+# ------------------------------------------------------------------------------- fused blocks
+def _layer_spec(i, w, pool=True):
+    spec = {"kernel": w["kernel"], "padding": 'SAME', "biases": w["biases"]}
+    if "gamma" in w:
+        spec.update(mean=w["moving_mean"], variance=w["moving_variance"], gamma=w["gamma"], epsilon=1e-5, leaky=True)
+    p = POOLS[i] if pool else None
+    spec["pool"] = None if p is None else (p[0], p[1], 'SAME')
+    return spec
+
+
+def _oracle_block(i, w, x, pool=True):
+    c = chain.Chain("oracle")
+    cur = c.create_input(x.shape)
+    cur = c.create_conv2d(cur, w["kernel"], [1, 1, 1, 1], 'SAME')
+    cur = c.create_bias_add(cur, w["biases"])
+    if "gamma" in w:
+        cur = c.create_batch_norm(cur, w["moving_mean"], w["moving_variance"], w["gamma"], 1e-5)
+        cur = c.create_leaky_relu(cur)
+    if pool and POOLS[i] is not None:
+        k, s = POOLS[i]
+        cur = c.create_max_pool2d(cur, [1, k, k, 1], [1, s, s, 1], 'SAME')
+    return c.run(x)
+
+
+# (layer, batch): batches chosen so the last tile of every tiling is ragged
+LAYER_CASES = [(0, 2), (1, 2), (2, 3), (3, 9), (4, 33), (5, 3), (6, 3), (7, 2), (8, 3)]
+HW = [416, 208, 104, 52, 26, 13, 13, 13, 13]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("layer,batch", LAYER_CASES)
+def test_each_yolo_block_fused_vs_oracle(oracle_libs, layer, batch, precision):
+    w = make_weights(20 + layer, negative_gamma=True)[layer]
+    rng = np.random.default_rng(40 + layer)
+    x = rng.standard_normal((batch, HW[layer], HW[layer], CHANNELS[layer])).astype(np.float32)
+    net = _lib.Net(x.shape, [_layer_spec(layer, w)], precision=precision)
+    info = net.block_info(0)
+    got = net.forward(x)
+    ref = _oracle_block(layer, w, x)
+    assert got.shape == ref.shape
+    err = normalised_error(got, ref)
+    print("layer %d %s: kernel=%s err=%.3g" % (layer, precision, info["kernel"], err))
+    if layer == 0:
+        assert info["kernel"] == "simt"                 # 3 channels: below TMA's 16-byte rule
+    elif layer <= 4:
+        assert info["kernel"] == "umma_tiled_pool" and info["pool_fused"]
+    else:
+        assert info["kernel"] == "umma_im2col"
+        assert info["pool_separate"] == (layer == 5)
+    assert err < (2e-3 if precision == "tf32" else 1.2e-2)
+    net.close()
+
+
+@pytest.mark.parametrize("layer,batch", [(1, 1), (3, 8), (4, 5)])
+def test_fused_pool_picks_the_reference_maximum(oracle_libs, layer, batch):
+    """Operator-local max-pool identity: given the SAME pre-pool tensor (the fused kernel's own
+    activations, obtained from the identical block without its pool), the fused 2x2/2 pool must
+    return exactly what the oracle's max_pool2d returns, hence the same window index."""
+    w = make_weights(30 + layer)[layer]
+    x = np.random.default_rng(50 + layer).standard_normal((batch, HW[layer], HW[layer], CHANNELS[layer])).astype(np.float32)
+    pooled = _lib.Net(x.shape, [_layer_spec(layer, w)], precision="tf32").forward(x)
+    prepool = _lib.Net(x.shape, [_layer_spec(layer, w, pool=False)], precision="tf32").forward(x)
+    ref, ref_idx = chain.pool_argmax(prepool, 2, 2)
+    np.testing.assert_array_equal(pooled, ref)
+    b, h, w_, c = prepool.shape
+    win = prepool.reshape(b, h // 2, 2, w_ // 2, 2, c).transpose(0, 1, 3, 5, 2, 4).reshape(b, h // 2, w_ // 2, c, 4)
+    got_idx = (win == pooled[..., None]).argmax(-1)       # first position holding the returned value
+    np.testing.assert_array_equal(got_idx, ref_idx)
+
+
+# ------------------------------------------------------------------------------- end to end
+def _yolo_engine(batch, precision, wseed=0, debug=False):
+    g = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g, [batch, 416, 416, 3], make_weights(wseed))
+    return dnn_b200.DnnInferenceEngine(g, debug, precision=precision)
+
+
+def _class_argmax(out):
+    return out.reshape(out.shape[0], 13, 13, 5, 25)[..., 5:].argmax(-1)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp32"])
+@pytest.mark.parametrize("wseed,iseed", [(0, 100), (1, 101)])
+def test_yolo_batch1_against_reference_golden(precision, wseed, iseed):
+    gold = np.load(os.path.join(GOLDEN, "yolo_w%d_i%d.npz" % (wseed, iseed)))
+    eng = _yolo_engine(1, precision, wseed)
+    out = eng.run(make_images(1, seed=iseed))
+    ref = gold["out_openblas"]
+    assert out.shape == (1, 13, 13, 125) and out.dtype == np.float32
+    err = normalised_error(out, ref)
+    plan = [p["kernel"] for p in eng.kernel_plan()]
+    print("yolo b1 %s w%d: err=%.3g plan=%s" % (precision, wseed, err, plan))
+    assert err < TOL[precision]
+    if precision != "fp32":
+        assert plan == ["simt"] + ["umma_tiled_pool"] * 4 + ["umma_im2col"] * 4
+    # argmax of detections: identical except on genuine near-ties
+    a, r = _class_argmax(out), _class_argmax(ref)
+    cls_ref = ref.reshape(1, 13, 13, 5, 25)[..., 5:]
+    bad = np.argwhere(a != r)
+    bound = 2 * err * np.abs(ref).max()
+    for idx in bad:
+        logits = cls_ref[tuple(idx)]
+        top2 = np.sort(logits)[-2:]
+        assert top2[1] - top2[0] <= bound, "argmax flip that is not a near-tie"
+    print("   class-argmax mismatches: %d of %d (all near-ties)" % (len(bad), a.size))
+    if precision == "fp32":
+        assert len(bad) == 0
+    eng.close()
+
+
+def test_yolo_block_outputs_layerwise_against_oracle(oracle_libs):
+    """Layer-wise comparison at block granularity (the reference's layer_N convention, restricted
+    to the tensors that still exist after fusion)."""
+    weights = make_weights(0)
+    x = make_images(1, seed=100)
+    _, nodes = chain.yolo_forward(weights, x, "oracle", keep=True)
+    eng = _yolo_engine(1, "tf32")
+    eng.run(x)
+    ends = [5, 10, 15, 20, 25, 30, 34, 38, 40]           # index of each block's last node
+    for blk, (node, res) in enumerate(eng.block_results().items()):
+        ref = nodes[ends[blk]]
+        assert res.shape == ref.shape
+        assert normalised_error(res, ref) < 5e-3, "block %d" % blk
+    eng.close()
+
+
+def test_batch_results_do_not_depend_on_batch_size(oracle_libs):
+    """Image i of a batch-5 run is bit-identical to a batch-1 run of image i (per-image math does
+    not depend on how the batch is tiled): the property multi-GPU sharding relies on."""
+    x = make_images(5, seed=200)
+    eng5 = _yolo_engine(5, "tf32")
+    out5 = eng5.run(x).copy()
+    eng1 = _yolo_engine(1, "tf32")
+    for i in (0, 3, 4):
+        np.testing.assert_array_equal(eng1.run(x[i:i + 1])[0], out5[i])
+    ref = chain.yolo_forward(make_weights(0), x[4:5], "oracle")
+    assert normalised_error(out5[4:5], ref) < TOL["tf32"]
+    out5b = eng5.run(x)
+    np.testing.assert_array_equal(out5, out5b)            # deterministic
+    eng5.close(); eng1.close()
+
+
+def test_full_size_batch256_properties(oracle_libs):
+    """BASELINE configs[2] size.  Size-independent checks: sampled images match the batch-1
+    engine bit for bit and the oracle within tolerance; no NaN/Inf anywhere."""
+    B = 256
+    x = make_images(B, seed=1000)
+    eng = _yolo_engine(B, "tf32")
+    out = eng.run(x)
+    assert out.shape == (B, 13, 13, 125) and np.isfinite(out).all()
+    eng1 = _yolo_engine(1, "tf32")
+    for i in (0, 127, 255):
+        np.testing.assert_array_equal(eng1.run(x[i:i + 1])[0], out[i])
+    ref = chain.yolo_forward(make_weights(0), x[255:256], "oracle")
+    assert normalised_error(out[255:256], ref) < TOL["tf32"]
+    eng.close(); eng1.close()
+
+
+def test_debug_mode_runs_node_by_node_and_dumps_layers(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    gold = np.load(os.path.join(GOLDEN, "mini_net.npz"))
+    weights = make_weights(5, channels=[3, 8, 16, 10], ksizes=[3, 3, 1], negative_gamma=True)
+    x = make_images(1, seed=55, hw=13)
+    g = dnn_b200.DnnGraphBuilder()
+    cur = g.create_input(list(x.shape))
+    for i, w in enumerate(weights):
+        cur = g.create_conv2d(cur, w["kernel"], [1, 1, 1, 1], 'SAME')
+        cur = g.create_bias_add(cur, w["biases"])
+        if i < 2:
+            cur = g.create_batch_norm(cur, w["moving_mean"], w["moving_variance"], w["gamma"], 1e-5)
+            cur = g.create_leaky_relu(cur)
+            cur = g.create_max_pool2d(cur, [1, 2, 2, 1], [1, 2 - i, 2 - i, 1], 'SAME')
+    g.set_out_node(cur)
+    out = dnn_b200.DnnInferenceEngine(g, True).run(x)
+    n_nodes = len(gold.files)
+    for i in range(n_nodes):
+        got = np.load(tmp_path / "intermediate" / ("layer_%d.npy" % i))
+        np.testing.assert_allclose(got, gold["node_%02d" % i], rtol=1e-5, atol=1e-5, err_msg="layer %d" % i)
+    np.testing.assert_allclose(out, gold["node_%02d" % (n_nodes - 1)], rtol=1e-5, atol=1e-5)
+    # the same graph, fused (small odd shapes -> CUDA-core kernels + separate pools): same answer
+    fused = dnn_b200.DnnInferenceEngine(g, False, precision="fp32").run(x)
+    np.testing.assert_allclose(fused, out, rtol=1e-4, atol=1e-4)
+    fused_tf32 = dnn_b200.DnnInferenceEngine(g, False, precision="tf32").run(x)
+    assert normalised_error(fused_tf32, out) < 5e-3
+
+
+def test_errors_are_reported_not_swallowed():
+    with pytest.raises(RuntimeError, match="device 99"):
+        _lib.Net((1, 8, 8, 4), [{"kernel": np.zeros((3, 3, 4, 4), np.float32)}], device=99)
+    with pytest.raises(RuntimeError, match="input channels"):
+        _lib.Net((1, 8, 8, 4), [{"kernel": np.zeros((3, 3, 5, 4), np.float32)}])
+
+
+def test_tensor_pipe_peak_probe_runs():
+    tf32 = _lib.measure_mma_peak("tf32")
+    bf16 = _lib.measure_mma_peak("bf16")
+    print("tcgen05 peak: tf32 %.0f TFLOP/s, bf16 %.0f TFLOP/s" % (tf32, bf16))
+    assert 300 < tf32 < 1400 and 600 < bf16 < 2800
