@@ -229,7 +229,10 @@ def run_b200(args):
     x = torch.rand((n_mb, mb, 416, 416, 3), device=dev, dtype=torch.float32, generator=gen)
     y = torch.empty((n_mb, mb, 13, 13, 125), device=dev, dtype=torch.float32)
     gathered = [torch.empty_like(y) for _ in range(world)] if (world > 1 and rank == 0) else None
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the network's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
 
     def step():
         for j in range(n_mb):

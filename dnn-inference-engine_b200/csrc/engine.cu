@@ -154,6 +154,8 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(false, false, 256, 128, 1, false, true),
     UMMA_ENTRY(false, false, 256, 128, 1, true, false),
     UMMA_ENTRY(false, false, 128, 128, 1, true, false),
+    UMMA_ENTRY(false, false, 64, 128, 1, true, false),
+    UMMA_ENTRY(false, false, 32, 64, 3, true, false),
     // BF16 operands, bf16 storage out
     UMMA_ENTRY(true, true, 32, 32, 3, false, true),
     UMMA_ENTRY(true, true, 64, 64, 3, false, true),
@@ -161,6 +163,8 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(true, true, 256, 128, 1, false, true),
     UMMA_ENTRY(true, true, 256, 128, 1, true, false),
     UMMA_ENTRY(true, true, 128, 128, 1, true, false),
+    UMMA_ENTRY(true, true, 64, 64, 3, true, false),
+    UMMA_ENTRY(true, true, 32, 32, 3, true, false),
     // BF16 operands, fp32 out (a network's last block)
     UMMA_ENTRY(true, false, 32, 32, 3, false, true),
     UMMA_ENTRY(true, false, 64, 64, 3, false, true),
@@ -168,6 +172,8 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(true, false, 256, 128, 1, false, true),
     UMMA_ENTRY(true, false, 256, 128, 1, true, false),
     UMMA_ENTRY(true, false, 128, 128, 1, true, false),
+    UMMA_ENTRY(true, false, 64, 64, 3, true, false),
+    UMMA_ENTRY(true, false, 32, 32, 3, true, false),
 };
 
 const UmmaEntry *find_umma(const UmmaKey &k) {
