@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/dnn_b200.h"
+#include "conv0_umma.cuh"
 #include "conv_umma.cuh"
 #include "ops_simt.cuh"
 
@@ -201,6 +202,8 @@ struct Block {
     bool in_bf16 = false, out_bf16 = false;     // storage types
     bool round_tf32 = false;
     const UmmaEntry *umma = nullptr;
+    bool op_bf16 = false;                       // conv0: MMA operand type (its input is always fp32)
+    conv0::Params c0{};
     umma_conv::Params up{};
     CUtensorMap map_a{}, map_b{};
     const void *map_a_base = nullptr;           // input pointer the A map was encoded for
@@ -298,6 +301,25 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     b.pool_fused = false;
     const bool force_simt = getenv("DNNB_FORCE_SIMT") != nullptr;
 
+    // first block straight from the raw 3-channel fp32 image: the patch-resident tcgen05 kernel
+    if (i == 0 && !in_bf16 && net->precision != DNNB_FP32 && !force_simt && !getenv("DNNB_NO_CONV0") && b.ic == 3 &&
+        b.oc == 16 && b.kh == 3 && b.kw == 3 && b.same && b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 &&
+        b.iw % 4 == 0) {
+        b.family = DNNB_KERNEL_UMMA_CONV0;
+        b.pool_fused = true;
+        b.pool_separate = false;
+        b.op_bf16 = want_bf16;
+        conv0::Params &c = b.c0;
+        c = conv0::Params{};
+        c.B = net->B; c.H = b.ih; c.W = b.iw;
+        c.col_tiles = (b.iw + 127) / 128;
+        c.num_tiles = net->B * (b.ih / 2) * c.col_tiles;
+        c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
+        b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
+        b.bn = 16; b.swz = 0;
+        return;
+    }
+
     if (net->precision != DNNB_FP32 && !force_simt && b.same && b.ch == b.ih && b.cw == b.iw) {
         const int es = in_bf16 ? 2 : 4;
         const int row_bytes = b.ic * es;
@@ -355,6 +377,20 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     b.pool_separate = b.pool_k > 0 && !b.pool_fused;
 }
 
+template <bool BF16, bool OUT_BF16>
+cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
+    auto kern = conv0::conv0_kernel<BF16, OUT_BF16>;
+    const int smem = conv0::kSmemBytes + 128;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, conv0::kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_conv0(const conv0::Params &p, bool bf16, bool out_bf16, int grid, cudaStream_t st) {
+    if (bf16) return out_bf16 ? launch_conv0_t<true, true>(p, grid, st) : launch_conv0_t<true, false>(p, grid, st);
+    return out_bf16 ? launch_conv0_t<false, true>(p, grid, st) : launch_conv0_t<false, false>(p, grid, st);
+}
+
 template <typename TIn, typename TOut>
 cudaError_t launch_simt_conv(const simt::ConvParams &p, cudaStream_t st) {
     dim3 grid((unsigned)(p.B * p.tiles_y * p.tiles_x), (unsigned)((p.OC + 63) / 64));
@@ -394,6 +430,11 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         p.leaky = b.leaky; p.pool = b.pool_fused; p.round_tf32 = b.round_tf32;
         p.tiles_y = (b.ch + 7) / 8; p.tiles_x = (b.cw + 7) / 8;
         CK(run_simt_conv(p, b.in_bf16, b.out_bf16, st));
+    } else if (b.family == DNNB_KERNEL_UMMA_CONV0) {
+        conv0::Params p = b.c0;
+        p.in = static_cast<const float *>(in); p.out = conv_out; p.wpack = b.d_wpack;
+        p.scale = b.d_scale; p.shift = b.d_shift;
+        CK(launch_conv0(p, b.op_bf16, b.out_bf16, b.grid, st));
     } else {
         if (b.map_a_base != in) {
             if (encode_map_a(net, b, in)) return 1;
@@ -414,7 +455,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
 int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st) {
     const void *cur = dev_in;
     Block &first = net->blocks.front();
-    if (first.family != DNNB_KERNEL_SIMT) {
+    if (first.family != DNNB_KERNEL_SIMT && first.family != DNNB_KERNEL_UMMA_CONV0) {
         // a tcgen05 first block reads its storage type: TF32-rounded fp32, or bf16
         const size_t n = (size_t)net->B * net->H * net->W * net->C;
         const int grid = ew_grid(n, net->num_sms);
@@ -653,9 +694,12 @@ int dnnb_net_finalize(dnnb_net *net) {
             if (b.oh <= 0 || b.ow <= 0) return fail("block %zu: empty pool output", i);
         }
         if (i == 0 && net->precision == DNNB_BF16) {
-            // would the first block run on tcgen05?  then its input is cast to bf16 first
-            plan_block(net, i, true);
-            if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
+            // conv0 reads the fp32 image itself; any other tcgen05 first block gets a bf16 cast
+            plan_block(net, i, false);
+            if (b.family != DNNB_KERNEL_UMMA_CONV0) {
+                plan_block(net, i, true);
+                if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
+            }
         } else {
             plan_block(net, i, in_bf16);
         }
@@ -666,7 +710,7 @@ int dnnb_net_finalize(dnnb_net *net) {
         if (b.pool_separate) CK(cudaMalloc(&b.d_conv_out, b.conv_out_elems * es_out));
         else b.d_conv_out = b.d_out;
         // epilogue constants, padded to the N tiling
-        const int ocp = b.family == DNNB_KERNEL_SIMT ? b.oc : b.up.num_n_tiles * b.bn;
+        const int ocp = (b.family == DNNB_KERNEL_SIMT || b.family == DNNB_KERNEL_UMMA_CONV0) ? b.oc : b.up.num_n_tiles * b.bn;
         std::vector<float> sc(ocp, 0.f), sh(ocp, 0.f);
         memcpy(sc.data(), b.scale.data(), sizeof(float) * b.oc);
         memcpy(sh.data(), b.shift.data(), sizeof(float) * b.oc);
@@ -674,10 +718,17 @@ int dnnb_net_finalize(dnnb_net *net) {
         CK(cudaMalloc(&b.d_shift, sizeof(float) * ocp));
         CK(cudaMemcpy(b.d_scale, sc.data(), sizeof(float) * ocp, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(b.d_shift, sh.data(), sizeof(float) * ocp, cudaMemcpyHostToDevice));
-        if (b.family == DNNB_KERNEL_SIMT) {
+        if (b.family == DNNB_KERNEL_UMMA_CONV0) {
+            std::vector<uint8_t> pk(conv0::kWBytes);
+            if (b.op_bf16) conv0::pack_weights<uint16_t>(b.kernel.data(), reinterpret_cast<uint16_t *>(pk.data()), host_bf16);
+            else conv0::pack_weights<float>(b.kernel.data(), reinterpret_cast<float *>(pk.data()), host_round_tf32);
+            CK(cudaMalloc(&b.d_wpack, conv0::kWBytes));
+            CK(cudaMemcpy(b.d_wpack, pk.data(), conv0::kWBytes, cudaMemcpyHostToDevice));
+        } else if (b.family == DNNB_KERNEL_SIMT) {
             CK(cudaMalloc(&b.d_kernel, sizeof(float) * b.kernel.size()));
             CK(cudaMemcpy(b.d_kernel, b.kernel.data(), sizeof(float) * b.kernel.size(), cudaMemcpyHostToDevice));
         } else {
+            if (b.family != DNNB_KERNEL_UMMA_TILED && b.family != DNNB_KERNEL_UMMA_IM2COL) return fail("internal: unknown kernel family");
             // prepack HWIO -> [tap][OCp][IC], K-major, rounded once to the MMA operand type
             const int taps = b.kh * b.kw;
             const size_t n = (size_t)taps * ocp * b.ic;
@@ -707,13 +758,13 @@ int dnnb_net_finalize(dnnb_net *net) {
     const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
     CK(cudaMalloc(&net->d_in, n_in * 4));
     Block &first = net->blocks.front();
-    if (first.family != DNNB_KERNEL_SIMT) {
+    if (first.family != DNNB_KERNEL_SIMT && first.family != DNNB_KERNEL_UMMA_CONV0) {
         CK(cudaMalloc(&net->d_in_cast, n_in * (first.in_bf16 ? 2 : 4)));
         net->launches += 1;
         if (encode_map_a(net, first, net->d_in_cast)) return 1;
     }
     for (size_t i = 1; i < net->blocks.size(); ++i)
-        if (net->blocks[i].family != DNNB_KERNEL_SIMT)
+        if (net->blocks[i].family == DNNB_KERNEL_UMMA_TILED || net->blocks[i].family == DNNB_KERNEL_UMMA_IM2COL)
             if (encode_map_a(net, net->blocks[i], net->blocks[i - 1].d_out)) return 1;
     Block &lastb = net->blocks.back();
     if (lastb.out_bf16) return fail("internal: last block stored as bf16");
@@ -813,7 +864,7 @@ int dnnb_net_time_blocks(dnnb_net *net, int warmup, int iters, float *ms) {
     cudaStream_t st = net->stream;
     // one full forward first so every block has a real input
     if (forward_impl(net, net->d_in, nullptr, st)) return 1;
-    const void *cur = net->blocks.front().family != DNNB_KERNEL_SIMT ? net->d_in_cast : (const void *)net->d_in;
+    const void *cur = net->d_in_cast ? net->d_in_cast : (const void *)net->d_in;
     for (size_t i = 0; i < net->blocks.size(); ++i) {
         Block &b = net->blocks[i];
         double total = 0.0;

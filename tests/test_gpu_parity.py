@@ -147,7 +147,7 @@ def test_each_yolo_block_fused_vs_oracle(oracle_libs, layer, batch, precision):
     err = normalised_error(got, ref)
     print("layer %d %s: kernel=%s err=%.3g" % (layer, precision, info["kernel"], err))
     if layer == 0:
-        assert info["kernel"] == "simt"                 # 3 channels: below TMA's 16-byte rule
+        assert info["kernel"] == "umma_conv0" and info["pool_fused"]   # 3 channels: patch-resident kernel
     elif layer <= 4:
         assert info["kernel"] == "umma_tiled_pool" and info["pool_fused"]
     else:
@@ -198,7 +198,7 @@ def test_yolo_batch1_against_reference_golden(precision, wseed, iseed):
     print("yolo b1 %s w%d: err=%.3g plan=%s" % (precision, wseed, err, plan))
     assert err < TOL[precision]
     if precision != "fp32":
-        assert plan == ["simt"] + ["umma_tiled_pool"] * 4 + ["umma_im2col"] * 4
+        assert plan == ["umma_conv0"] + ["umma_tiled_pool"] * 4 + ["umma_im2col"] * 4
     # argmax of detections: identical except on genuine near-ties
     a, r = _class_argmax(out), _class_argmax(ref)
     cls_ref = ref.reshape(1, 13, 13, 5, 25)[..., 5:]
