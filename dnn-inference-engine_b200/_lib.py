@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libdnn_b200.so")
 
 TF32, BF16, FP32 = 0, 1, 2
 PRECISIONS = {"tf32": TF32, "bf16": BF16, "fp32": FP32}
-KERNEL_NAMES = {0: "simt", 1: "umma_tiled_pool", 2: "umma_im2col", 3: "umma_conv0"}
+KERNEL_NAMES = {0: "simt", 1: "umma_tiled_pool", 2: "umma_im2col", 3: "umma_conv0", 4: "umma_rowpair"}
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(LIB_PATH + " is missing: build it with `python dnn-inference-engine_b200/build.py` "
@@ -54,6 +54,7 @@ _sig("dnnb_net_forward_device", c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("dnnb_net_sync", c_void_p)
 _sig("dnnb_net_block_output", c_void_p, c_int, FP)
 _sig("dnnb_net_block_info", c_void_p, c_int, IP)
+_sig("dnnb_net_debug_prepool", c_void_p, c_int, FP)
 _sig("dnnb_net_time_blocks", c_void_p, c_int, c_int, FP)
 _sig("dnnb_net_launches_per_forward", c_void_p, IP)
 _sig("dnnb_net_profile_block", c_void_p, c_int)
@@ -66,7 +67,7 @@ _sig("dnnb_measure_mma_peak", c_int, c_int, FP)
 EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
-           "dnnb_net_forward_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info",
+           "dnnb_net_forward_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak"]
 
@@ -190,6 +191,13 @@ class Net:
         shape = self.block_info(i)["out_shape"]
         out = np.empty(shape, dtype=np.float32)
         check(lib.dnnb_net_block_output(self._h, i, fptr(out)))
+        return out
+
+    def debug_prepool(self, i, conv_hw):
+        """Pre-pool activations of a block whose pool is fused (see dnnb_net_debug_prepool)."""
+        info = self.block_info(i)
+        out = np.empty((self.in_shape[0], conv_hw[0], conv_hw[1], info["out_shape"][3]), dtype=np.float32)
+        check(lib.dnnb_net_debug_prepool(self._h, i, fptr(out)))
         return out
 
     def time_blocks(self, warmup=3, iters=10):

@@ -17,8 +17,8 @@
 // epilogue thread of lane m therefore holds both rows of pixel column m: the vertical max is
 // thread-local, the horizontal max one shuffle.
 //
-// Warp roles (448 threads): 5 producer warps (each builds whole patches, tile t -> warp t % 5, so
-// five global-load latencies overlap), 1 MMA warp, 2 x 4 epilogue warps (alternate tiles).
+// Warp roles (448 threads): 4 producer warps (each builds whole patches, tile t -> warp t % 4, so
+// four global-load latencies overlap), 2 MMA warps and 2 x 4 epilogue warps (both alternate tiles).
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -27,10 +27,15 @@
 
 namespace conv0 {
 
-constexpr int kProducerWarps = 5;
+// Ring discipline: every patch stage is always filled by the same producer warp and drained by the
+// same MMA warp (kStages is a multiple of both warp counts), and every accumulator stage belongs to
+// one MMA warp and one epilogue group.  Each waiter therefore follows its barrier phase by phase; a
+// waiter that could get two phases ahead would see a stale parity as "done".
+constexpr int kProducerWarps = 4;
+constexpr int kMmaWarps = 2;       // tiles alternate between two issuing warps (small, issue-bound MMAs)
 constexpr int kEpilogueGroups = 2;
-constexpr int kThreads = (kProducerWarps + 1 + 4 * kEpilogueGroups) * 32;
-constexpr int kStages = 6;         // patch ring
+constexpr int kThreads = (kProducerWarps + kMmaWarps + 4 * kEpilogueGroups) * 32;
+constexpr int kStages = 8;         // patch ring
 constexpr int kAccStages = 4;      // TMEM accumulator ring, 32 columns each
 constexpr int kPatchPx = 136;      // pixels per patch row: [w0-4, w0+132)
 constexpr int kGroups = kPatchPx / 4;
@@ -38,6 +43,8 @@ constexpr int kPatchRowBytes = kPatchPx * 16;
 constexpr int kPatchBytes = 4 * kPatchRowBytes;
 constexpr int kWBytes = 8 * 1024;  // 8 weight operands (4 patch rows x 2 tap pairs), <= 32 x 8 x 4 B each
 constexpr int kSmemBytes = kStages * kPatchBytes + kWBytes + 1024 + 256;
+static_assert(kStages % kProducerWarps == 0 && kStages % kMmaWarps == 0, "one owner warp per stage");
+static_assert(kAccStages % kMmaWarps == 0 && kAccStages % kEpilogueGroups == 0, "one owner per accumulator stage");
 
 struct Params {
     const float *in;     // [B, H, W, 3] fp32
@@ -49,6 +56,7 @@ struct Params {
     int col_tiles;       // ceil(W / 128)
     int num_tiles;       // B * (H/2) * col_tiles
     int leaky, round_tf32;
+    float *prepool;      // debug: also dump the pre-pool activations [B,H,W,16] fp32
 };
 
 // no-swizzle K-major descriptor: LBO = byte distance between the two 16-byte K halves of one MMA,
@@ -152,34 +160,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
         }
-    } else if (warp == kProducerWarps) {
-        // ------------------------------------------------------------ MMA issuer
+    } else if (warp < kProducerWarps + kMmaWarps) {
+        // ------------------------------------------------------------ MMA issuers
         if (ptx::elect_one()) {
             constexpr uint32_t fmt = BF16 ? 1u : 2u;
             constexpr uint32_t idesc16 = ptx::umma_idesc(fmt, 16), idesc32 = ptx::umma_idesc(fmt, 32);
-            const uint32_t w_base = ptx::smem_u32(s_w);
-            for (int t = 0; t < my_tiles; ++t) {
+            // descriptor words: lo = start >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version; no swizzle
+            constexpr uint32_t HI = (128u >> 4) | (1u << 14);
+            const uint32_t w_lo0 = ptx::smem_u32(s_w) >> 4;
+            for (int t = warp - kProducerWarps; t < my_tiles; t += kMmaWarps) {
                 const int stage = t % kStages, acc = t % kAccStages;
                 ptx::mbar_wait(bar_tempty + 8 * acc, ((t / kAccStages) & 1) ^ 1);
                 ptx::mbar_wait(bar_full + 8 * stage, (t / kStages) & 1);
                 ptx::tc_fence_after();
-                const uint32_t patch = ptx::smem_u32(s_patch + stage * kPatchBytes);
+                const uint32_t a_lo0 = (ptx::smem_u32(s_patch + stage * kPatchBytes) >> 4) | ((16u >> 4) << 16);
                 const uint32_t d = tmem_base + acc * 32;
                 // patch rows 1 and 2 feed both output rows (N = 32), rows 0 and 3 one each (N = 16).
-                // Operand q = r*2 + pair lives at w_base + q*1024; LBO: 32 rows x 16 B = 512 (256 for N = 16).
+                // Operand q = r*2 + pair lives at s_w + q*1024; LBO: 32 rows x 16 B = 512 (256 for N = 16).
                 // Row 1 goes first so its N = 32 MMA initialises all 32 accumulator columns.
-                const int order[4] = {1, 2, 0, 3};
 #pragma unroll
                 for (int oi = 0; oi < 4; ++oi) {
-                    const int r = order[oi];
+                    const int r = oi == 0 ? 1 : oi == 1 ? 2 : oi == 2 ? 0 : 3;
                     const bool wide = r == 1 || r == 2;
 #pragma unroll
                     for (int pr = 0; pr < 2; ++pr) {
                         // A rows: pixel m, taps dj = 2*pr, 2*pr+1  ->  patch pixel m + dj + 3
-                        const uint64_t da = desc_noswz(patch + r * kPatchRowBytes + (3 + 2 * pr) * 16, 16, 128);
-                        const uint64_t db = desc_noswz(w_base + (r * 2 + pr) * 1024, wide ? 512 : 256, 128);
-                        const uint32_t dcol = d + (r == 3 ? 16 : 0);
-                        ptx::umma<BF16>(dcol, da, db, wide ? idesc32 : idesc16, (oi | pr) != 0 ? 1u : 0u);
+                        const uint32_t a_off = (r * kPatchRowBytes + (3 + 2 * pr) * 16) >> 4;
+                        const uint32_t b_lo = w_lo0 + (((r * 2 + pr) * 1024) >> 4) + (((wide ? 512u : 256u) >> 4) << 16);
+                        ptx::umma<BF16>(d + (r == 3 ? 16 : 0), ptx::umma_desc_join(a_lo0 + a_off, HI),
+                                        ptx::umma_desc_join(b_lo, HI), wide ? idesc32 : idesc16, (oi | pr) != 0 ? 1u : 0u);
                     }
                 }
                 ptx::umma_commit(bar_empty + 8 * stage);
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         }
     } else {
         // ------------------------------------------------------------ epilogue (two groups alternate tiles)
-        const int ew = warp - kProducerWarps - 1;
+        const int ew = warp - kProducerWarps - kMmaWarps;
         const int group = ew >> 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
         const int m = quarter * 32 + lane;            // pixel column within the tile
@@ -207,6 +216,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 32, raw);
                 ptx::tmem_ld_wait();
                 float v[16];
+                if (p.prepool != nullptr) {               // debug dump of the pooled-over activations (cold path)
+                    for (int c = 0; c < 16; ++c) {
+                        float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
+                        float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
+                        if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                        if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
+                        else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
+                        if (w < p.W) {
+                            p.prepool[(((size_t)n * p.H + 2 * j) * p.W + w) * 16 + c] = a;
+                            p.prepool[(((size_t)n * p.H + 2 * j + 1) * p.W + w) * 16 + c] = b;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);

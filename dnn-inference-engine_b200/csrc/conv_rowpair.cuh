@@ -1,0 +1,254 @@
+// conv_rowpair.cuh -- 3x3 SAME conv + bias/BatchNorm/LeakyReLU + 2x2/2 max-pool for the wide,
+// few-channel blocks (blocks 1 and 2 of proj3/yolov2tiny.py:36-46: 208x208x16->32, 104x104x32->64),
+// which are bound by memory traffic, not by the tensor pipe.
+//
+// conv_umma.cuh fetches one A tile per filter tap, i.e. it pulls every input pixel through L2
+// nine times.  Here the CTA loads a PATCH (4 input rows x 130 pixels, all channels: one TMA box,
+// zero-filled outside the image = SAME padding) once per tile and all nine taps are UMMA
+// descriptors that start at different rows of that patch: a swizzled K-major operand may start
+// at any row of a TMA-written slab (tools/probe_desc.cu, Q1/Q2).  The 3x3xICxOC weights stay
+// resident in shared memory for the whole kernel.
+//
+// Tile = output rows (2j, 2j+1) x 128 columns.  TMEM columns [0,OC) hold output row 2j and
+// [OC,2OC) row 2j+1; patch row r is multiplied once by the stacked weights
+// [W(di=r) | W(di=r-1)] (N = 2*OC; N = OC for r = 0 and r = 3).  The epilogue thread of lane m
+// holds both rows of pixel column m: vertical max in registers, horizontal max by one shuffle.
+//
+// CTA = 352 threads: warp 0 TMA producer, warps 1-2 MMA issuers (alternate tiles; warp 1 owns TMEM),
+// 2 x 4 epilogue warps that alternate tiles.  One channel chunk only: IC * elem_size must equal the swizzle span (32/64/128 B).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace rowpair {
+
+constexpr int kMmaWarps = 2;      // tiles alternate between two issuing warps: the MMAs are small, issue-bound
+constexpr int kThreads = (1 + kMmaWarps + 8) * 32;
+constexpr int kPatchW = 130;      // 128 columns + left/right halo
+constexpr int kPatchRows = 4;     // 2 output rows + top/bottom halo
+
+struct Params {
+    int B, H, W;          // conv output = input spatial size
+    int col_tiles;        // ceil(W / 128)
+    int num_tiles;        // B * (H/2) * col_tiles
+    const float *scale;   // [OC]
+    const float *shift;   // [OC]
+    void *out;            // [B, H/2, W/2, OC]
+    int leaky, round_tf32;
+    float *prepool;       // debug: also dump the pre-pool activations [B,H,W,OC] fp32
+};
+
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
+
+template <int OC, int SWZ>
+struct Cfg {
+    static constexpr int PATCH_ROW = kPatchW * SWZ;
+    static constexpr int PATCH_RAW = kPatchRows * PATCH_ROW;
+    static constexpr int PATCH_BYTES = (PATCH_RAW + 1023) / 1024 * 1024;
+    static constexpr int W_DJ_BYTES = 3 * OC * SWZ;            // one dj: rows [di=2 | di=1 | di=0] x OC
+    static constexpr int W_BYTES = 3 * W_DJ_BYTES;
+    static constexpr int TAIL_BYTES = 1024 + 2 * OC * 4;
+    static constexpr int BUDGET = 227 * 1024 - 1024;
+    static constexpr int STAGES = cmin(4, (BUDGET - W_BYTES - TAIL_BYTES) / PATCH_BYTES);
+    static constexpr int SMEM_BYTES = STAGES * PATCH_BYTES + W_BYTES + TAIL_BYTES + 1024;
+    static constexpr int ACC_COLS = 2 * OC;
+    static constexpr int ACC_STAGES = cmin(4, 512 / ACC_COLS);
+    static constexpr int TMEM_COLS = pow2_at_least(ACC_COLS * ACC_STAGES);
+    static_assert(STAGES >= 2, "need two patch stages");
+    // one owner per ring slot (see conv0_umma.cuh): stages and accumulators never change their MMA warp
+    static_assert(STAGES % kMmaWarps == 0 && ACC_STAGES % kMmaWarps == 0, "one owner warp per ring slot");
+    static_assert(ACC_STAGES >= 2 && TMEM_COLS <= 512, "need two accumulator stages");
+    static_assert(W_DJ_BYTES % 1024 == 0, "weight slabs must keep the swizzle phase");
+    static_assert(OC % 16 == 0 && 3 * OC <= 256, "weights of one dj must fit one TMA box");
+};
+
+template <bool BF16, bool OUT_BF16, int OC, int SWZ>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                    const Params p) {
+    using C = Cfg<OC, SWZ>;
+    constexpr int STAGES = C::STAGES, ACC = C::ACC_STAGES;
+    constexpr int KC = SWZ / 32;                     // MMAs along K per tap (32 bytes of K each)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *s_w = smem + STAGES * C::PATCH_BYTES;
+    uint8_t *tail = s_w + C::W_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail);     // full[S], empty[S], tfull[A], tempty[A], wbar
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
+    float *s_scale = reinterpret_cast<float *>(tail + 1024);
+    float *s_shift = s_scale + OC;
+
+    const uint32_t patch_base = ptx::smem_u32(smem);
+    const uint32_t w_base = ptx::smem_u32(s_w);
+    const uint32_t bar_full = ptx::smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES;
+    const uint32_t bar_tempty = bar_tfull + 8 * ACC;
+    const uint32_t bar_w = bar_tempty + 8 * ACC;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows2 = p.H >> 1;
+    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_w);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < ACC; ++s) { ptx::mbar_init(bar_tfull + 8 * s, 1); ptx::mbar_init(bar_tempty + 8 * s, 128); }
+        ptx::mbar_init(bar_w, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    for (int i = threadIdx.x; i < OC; i += kThreads) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(bar_w, C::W_BYTES);                 // resident weights, once
+            for (int dj = 0; dj < 3; ++dj) ptx::tma_load_3d(w_base + dj * C::W_DJ_BYTES, &map_w, bar_w, 0, 0, dj);
+            for (int t = 0; t < my_tiles; ++t) {
+                const int tile = blockIdx.x + t * gridDim.x;
+                const int ct = tile % p.col_tiles;
+                const int j = (tile / p.col_tiles) % rows2;
+                const int n = tile / (p.col_tiles * rows2);
+                const int stage = t % STAGES;
+                ptx::mbar_wait(bar_empty + 8 * stage, ((t / STAGES) & 1) ^ 1);
+                ptx::mbar_expect_tx(bar_full + 8 * stage, C::PATCH_RAW);
+                ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, ct * 128 - 1,
+                                 2 * j - 1, n);
+            }
+        }
+    } else if (warp <= kMmaWarps) {
+        // ------------------------------------------------------------ MMA issuers
+        if (ptx::elect_one()) {
+            constexpr uint32_t fmt = BF16 ? 1u : 2u;
+            constexpr uint32_t idesc_wide = ptx::umma_idesc(fmt, 2 * OC), idesc_narrow = ptx::umma_idesc(fmt, OC);
+            constexpr uint32_t HI = ptx::umma_desc_hi(SWZ);
+            const uint32_t b_lo0 = ptx::umma_desc_lo(w_base);
+            ptx::mbar_wait(bar_w, 0);
+            for (int t = warp - 1; t < my_tiles; t += kMmaWarps) {
+                const int stage = t % STAGES, acc = t % ACC;
+                ptx::mbar_wait(bar_tempty + 8 * acc, ((t / ACC) & 1) ^ 1);
+                ptx::mbar_wait(bar_full + 8 * stage, (t / STAGES) & 1);
+                ptx::tc_fence_after();
+                const uint32_t a_lo0 = ptx::umma_desc_lo(patch_base + stage * C::PATCH_BYTES);
+                const uint32_t d = tmem_base + acc * C::ACC_COLS;
+                // weight rows of one dj slab: [W(di=2) | W(di=1) | W(di=0)], OC rows each.
+                //   r=1: rows OC..3OC   = [W1|W0] -> cols [0,2OC)      r=2: rows 0..2OC = [W2|W1] -> cols [0,2OC)
+                //   r=0: rows 2OC..3OC  =  W0     -> cols [0,OC)       r=3: rows 0..OC  =  W2     -> cols [OC,2OC)
+                // r=1 first: its N = 2*OC MMA initialises every accumulator column.
+                // Every descriptor is (per-tile base) + (compile-time constant), in 16-byte units.
+#pragma unroll
+                for (int oi = 0; oi < 4; ++oi) {
+                    const int r = oi == 0 ? 1 : oi == 1 ? 2 : oi == 2 ? 0 : 3;
+                    const int wrow = r == 0 ? 2 * OC : r == 1 ? OC : 0;
+                    const bool wide = r == 1 || r == 2;
+                    const uint32_t dcol = d + (r == 3 ? OC : 0);
+#pragma unroll
+                    for (int dj = 0; dj < 3; ++dj) {
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const uint32_t a_off = ((r * kPatchW + dj) * SWZ + 32 * k) >> 4;
+                            const uint32_t b_off = (dj * C::W_DJ_BYTES + wrow * SWZ + 32 * k) >> 4;
+                            ptx::umma<BF16>(dcol, ptx::umma_desc_join(a_lo0 + a_off, HI), ptx::umma_desc_join(b_lo0 + b_off, HI),
+                                            wide ? idesc_wide : idesc_narrow, (oi | dj | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                ptx::umma_commit(bar_empty + 8 * stage);
+                ptx::umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (two groups alternate tiles)
+        const int group = (warp - 1 - kMmaWarps) >> 2;
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const int OW = p.W >> 1;
+        const bool odd = lane & 1;
+        for (int t = group; t < my_tiles; t += 2) {
+            const int tile = blockIdx.x + t * gridDim.x;
+            const int ct = tile % p.col_tiles;
+            const int j = (tile / p.col_tiles) % rows2;
+            const int n = tile / (p.col_tiles * rows2);
+            const int w = ct * 128 + m;
+            const int acc = t % ACC;
+            ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
+            ptx::tc_fence_after();
+            if (ct * 128 + quarter * 32 < p.W) {           // warp-uniform: skip quarters right of the image
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS;
+                const size_t pix = ((size_t)n * rows2 + j) * OW + (w >> 1);
+#pragma unroll 1
+                for (int c0 = 0; c0 < OC; c0 += 16) {
+                    uint32_t top[16], bot[16];
+                    ptx::tmem_ld_32x16(taddr + c0, top);         // output row 2j
+                    ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // output row 2j+1
+                    ptx::tmem_ld_wait();
+                    float v[16];
+                    if (p.prepool != nullptr && w < p.W) {     // debug dump of the pooled-over activations (cold path)
+                        for (int c = 0; c < 16; ++c) {
+                            const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
+                            float a = fmaf(__uint_as_float(top[c]), sc, sh);
+                            float b = fmaf(__uint_as_float(bot[c]), sc, sh);
+                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                            if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
+                            else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
+                            p.prepool[(((size_t)n * p.H + 2 * j) * p.W + w) * OC + c0 + c] = a;
+                            p.prepool[(((size_t)n * p.H + 2 * j + 1) * p.W + w) * OC + c0 + c] = b;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
+                        float a = fmaf(__uint_as_float(top[c]), sc, sh);
+                        float b = fmaf(__uint_as_float(bot[c]), sc, sh);
+                        if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                        float mx = fmaxf(a, b);                  // vertical max; rounding is monotone, so round after
+                        if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
+                        else if (p.round_tf32) mx = ptx::round_tf32(mx);
+                        v[c] = mx;
+                    }
+                    float r8[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float keep = odd ? v[8 + c] : v[c];
+                        const float send = odd ? v[c] : v[8 + c];
+                        r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                    }
+                    if (w < p.W) {
+                        const size_t off = pix * OC + c0 + (odd ? 8 : 0);
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                            *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.out) + off) = pk;
+                        } else {
+                            float *o = static_cast<float *>(p.out) + off;
+                            *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+                            *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace rowpair

@@ -48,6 +48,7 @@ struct Params {
     int OH, OW;           // stored spatial size (H/2, W/2 when the pool is fused)
     int leaky;
     int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
+    float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
 };
 
 template <int BN, int SWZ, int KBS>
@@ -207,6 +208,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
             bool valid;
             size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
+            size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
             if constexpr (IM2COL) {
                 const int m = m_tile * kBM + row;
                 valid = m < p.M_total;
@@ -222,6 +224,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 valid = n < p.B;
                 if constexpr (POOL) out_pix = ((size_t)n * p.OH + (h >> 1)) * p.OW + (w >> 1);
                 else out_pix = ((size_t)n * p.OH + h) * p.OW + w;
+                pre_pix = ((size_t)n * p.H + h) * p.W + w;
             }
 
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -258,6 +261,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
 
                 if constexpr (POOL) {
+                    if (p.prepool != nullptr && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.OC) p.prepool[pre_pix * p.OC + col0 + j] = v[j];
+                    }
                     // butterfly 2x2 max over lanes (w^1, then h^1 = lane ^ tw); each lane ends up
                     // with 8 of the 32 columns of its window: 16*(w&1) + 8*(h&1) + [0,8)
                     const bool wodd = lane & 1;

@@ -18,6 +18,7 @@
 
 #include "../../include/dnn_b200.h"
 #include "conv0_umma.cuh"
+#include "conv_rowpair.cuh"
 #include "conv_umma.cuh"
 #include "ops_simt.cuh"
 
@@ -186,6 +187,40 @@ const UmmaEntry *find_umma(const UmmaKey &k) {
 }
 
 // ------------------------------------------------------------------------------------------
+// patch-resident row-pair kernel instantiations (conv_rowpair.cuh)
+typedef cudaError_t (*RowpairLauncher)(const CUtensorMap &, const CUtensorMap &, const rowpair::Params &, int grid,
+                                       cudaStream_t);
+struct RowpairEntry {
+    bool bf16, out_bf16;
+    int oc, swz;
+    RowpairLauncher launch;
+    int stages;
+};
+
+template <bool BF16, bool OUT_BF16, int OC, int SWZ>
+cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const rowpair::Params &p, int grid,
+                           cudaStream_t st) {
+    using C = rowpair::Cfg<OC, SWZ>;
+    auto kern = rowpair::conv_rowpair_kernel<BF16, OUT_BF16, OC, SWZ>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, rowpair::kThreads, C::SMEM_BYTES, st>>>(ma, mw, p);
+    return cudaGetLastError();
+}
+#define ROWPAIR_ENTRY(BF16, OBF, OC, SWZ) \
+    {BF16, OBF, OC, SWZ, &launch_rowpair<BF16, OBF, OC, SWZ>, rowpair::Cfg<OC, SWZ>::STAGES}
+const RowpairEntry g_rowpair_table[] = {
+    ROWPAIR_ENTRY(false, false, 32, 64),  ROWPAIR_ENTRY(false, false, 64, 128),
+    ROWPAIR_ENTRY(true, true, 32, 32),    ROWPAIR_ENTRY(true, true, 64, 64),
+    ROWPAIR_ENTRY(true, false, 32, 32),   ROWPAIR_ENTRY(true, false, 64, 64),
+};
+const RowpairEntry *find_rowpair(bool bf16, bool out_bf16, int oc, int swz) {
+    for (const RowpairEntry &e : g_rowpair_table)
+        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.oc == oc && e.swz == swz) return &e;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
 struct Block {
     // description
     int kh = 0, kw = 0, ic = 0, oc = 0, same = 1;
@@ -204,6 +239,8 @@ struct Block {
     const UmmaEntry *umma = nullptr;
     bool op_bf16 = false;                       // conv0: MMA operand type (its input is always fp32)
     conv0::Params c0{};
+    const RowpairEntry *rowpair = nullptr;
+    rowpair::Params rp{};
     umma_conv::Params up{};
     CUtensorMap map_a{}, map_b{};
     const void *map_a_base = nullptr;           // input pointer the A map was encoded for
@@ -263,6 +300,11 @@ int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
         r = g_encode_im2col(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper, (cuuint32_t)bkc,
                             (cuuint32_t)umma_conv::kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz),
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
+        cuuint32_t box[4] = {(cuuint32_t)b.ic, (cuuint32_t)rowpair::kPatchW, (cuuint32_t)rowpair::kPatchRows, 1};
+        r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)b.up.tw, (cuuint32_t)b.up.th, (cuuint32_t)b.up.nb};
         r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
@@ -277,6 +319,17 @@ int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
 int encode_map_b(Block &b) {
     const int es = b.in_bf16 ? 2 : 4;
     const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
+        cuuint64_t dims[3] = {(cuuint64_t)b.ic, (cuuint64_t)(3 * b.oc), 3};
+        cuuint64_t strides[2] = {(cuuint64_t)b.ic * es, (cuuint64_t)3 * b.oc * b.ic * es};
+        cuuint32_t box[3] = {(cuuint32_t)b.ic, (cuuint32_t)(3 * b.oc), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = g_encode_tiled(&b.map_b, dt, 3, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("tensor-map encode (row-pair weights) failed: CUresult %d", (int)r);
+        return 0;
+    }
     const int ocp = b.up.num_n_tiles * b.bn;
     cuuint64_t dims[3] = {(cuuint64_t)b.ic, (cuuint64_t)ocp, (cuuint64_t)(b.kh * b.kw)};
     cuuint64_t strides[2] = {(cuuint64_t)b.ic * es, (cuuint64_t)ocp * b.ic * es};
@@ -318,6 +371,29 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
         b.bn = 16; b.swz = 0;
         return;
+    }
+
+    // wide few-channel pooled blocks: patch-resident row-pair kernel
+    if (net->precision != DNNB_FP32 && !force_simt && !getenv("DNNB_NO_ROWPAIR") && b.same && b.kh == 3 && b.kw == 3 &&
+        b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0) {
+        const int row_bytes = b.ic * (in_bf16 ? 2 : 4);
+        const RowpairEntry *e = (row_bytes == 32 || row_bytes == 64 || row_bytes == 128)
+                                    ? find_rowpair(in_bf16, b.out_bf16, b.oc, row_bytes) : nullptr;
+        if (e) {
+            b.family = DNNB_KERNEL_UMMA_ROWPAIR;
+            b.rowpair = e;
+            b.pool_fused = true;
+            b.pool_separate = false;
+            b.bn = b.oc; b.swz = row_bytes;
+            rowpair::Params &r = b.rp;
+            r = rowpair::Params{};
+            r.B = net->B; r.H = b.ih; r.W = b.iw;
+            r.col_tiles = (b.iw + 127) / 128;
+            r.num_tiles = net->B * (b.ih / 2) * r.col_tiles;
+            r.leaky = b.leaky; r.round_tf32 = b.round_tf32;
+            b.grid = r.num_tiles < net->num_sms ? r.num_tiles : net->num_sms;
+            return;
+        }
     }
 
     if (net->precision != DNNB_FP32 && !force_simt && b.same && b.ch == b.ih && b.cw == b.iw) {
@@ -418,7 +494,8 @@ cudaError_t run_pool(const simt::PoolParams &p, bool bf16, int num_sms, cudaStre
 }
 
 // launches the kernels of one block; `in` has the block's input storage type
-int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override, cudaStream_t st) {
+int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override, cudaStream_t st,
+              float *prepool = nullptr) {
     void *conv_out = b.d_conv_out;
     void *out = final_out_override ? final_out_override : b.d_out;
     if (!b.pool_separate) conv_out = out;
@@ -433,14 +510,21 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
     } else if (b.family == DNNB_KERNEL_UMMA_CONV0) {
         conv0::Params p = b.c0;
         p.in = static_cast<const float *>(in); p.out = conv_out; p.wpack = b.d_wpack;
-        p.scale = b.d_scale; p.shift = b.d_shift;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.prepool = prepool;
         CK(launch_conv0(p, b.op_bf16, b.out_bf16, b.grid, st));
+    } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
+        if (b.map_a_base != in) {
+            if (encode_map_a(net, b, in)) return 1;
+        }
+        rowpair::Params p = b.rp;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
+        CK(b.rowpair->launch(b.map_a, b.map_b, p, b.grid, st));
     } else {
         if (b.map_a_base != in) {
             if (encode_map_a(net, b, in)) return 1;
         }
         umma_conv::Params p = b.up;
-        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
         CK(b.umma->launch(b.map_a, b.map_b, p, b.grid, st));
     }
     if (b.pool_separate) {
@@ -710,7 +794,7 @@ int dnnb_net_finalize(dnnb_net *net) {
         if (b.pool_separate) CK(cudaMalloc(&b.d_conv_out, b.conv_out_elems * es_out));
         else b.d_conv_out = b.d_out;
         // epilogue constants, padded to the N tiling
-        const int ocp = (b.family == DNNB_KERNEL_SIMT || b.family == DNNB_KERNEL_UMMA_CONV0) ? b.oc : b.up.num_n_tiles * b.bn;
+        const int ocp = (b.family == DNNB_KERNEL_UMMA_TILED || b.family == DNNB_KERNEL_UMMA_IM2COL) ? b.up.num_n_tiles * b.bn : b.oc;
         std::vector<float> sc(ocp, 0.f), sh(ocp, 0.f);
         memcpy(sc.data(), b.scale.data(), sizeof(float) * b.oc);
         memcpy(sh.data(), b.shift.data(), sizeof(float) * b.oc);
@@ -724,6 +808,27 @@ int dnnb_net_finalize(dnnb_net *net) {
             else conv0::pack_weights<float>(b.kernel.data(), reinterpret_cast<float *>(pk.data()), host_round_tf32);
             CK(cudaMalloc(&b.d_wpack, conv0::kWBytes));
             CK(cudaMemcpy(b.d_wpack, pk.data(), conv0::kWBytes, cudaMemcpyHostToDevice));
+        } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
+            // [dj][(2-di)*OC + oc][IC]: for every dj the rows are W(di=2) | W(di=1) | W(di=0)
+            const size_t n = (size_t)9 * b.oc * b.ic;
+            std::vector<float> pk(n);
+            for (int di = 0; di < 3; ++di)
+                for (int dj = 0; dj < 3; ++dj)
+                    for (int c = 0; c < b.ic; ++c)
+                        for (int d = 0; d < b.oc; ++d)
+                            pk[((size_t)dj * 3 * b.oc + (size_t)(2 - di) * b.oc + d) * b.ic + c] =
+                                b.kernel[((size_t)(di * 3 + dj) * b.ic + c) * b.oc + d];
+            if (b.in_bf16) {
+                std::vector<uint16_t> h(n);
+                for (size_t q = 0; q < n; ++q) h[q] = host_bf16(pk[q]);
+                CK(cudaMalloc(&b.d_wpack, n * 2));
+                CK(cudaMemcpy(b.d_wpack, h.data(), n * 2, cudaMemcpyHostToDevice));
+            } else {
+                for (size_t q = 0; q < n; ++q) pk[q] = host_round_tf32(pk[q]);
+                CK(cudaMalloc(&b.d_wpack, n * 4));
+                CK(cudaMemcpy(b.d_wpack, pk.data(), n * 4, cudaMemcpyHostToDevice));
+            }
+            if (encode_map_b(b)) return 1;
         } else if (b.family == DNNB_KERNEL_SIMT) {
             CK(cudaMalloc(&b.d_kernel, sizeof(float) * b.kernel.size()));
             CK(cudaMemcpy(b.d_kernel, b.kernel.data(), sizeof(float) * b.kernel.size(), cudaMemcpyHostToDevice));
@@ -764,7 +869,8 @@ int dnnb_net_finalize(dnnb_net *net) {
         if (encode_map_a(net, first, net->d_in_cast)) return 1;
     }
     for (size_t i = 1; i < net->blocks.size(); ++i)
-        if (net->blocks[i].family == DNNB_KERNEL_UMMA_TILED || net->blocks[i].family == DNNB_KERNEL_UMMA_IM2COL)
+        if (net->blocks[i].family == DNNB_KERNEL_UMMA_TILED || net->blocks[i].family == DNNB_KERNEL_UMMA_IM2COL ||
+            net->blocks[i].family == DNNB_KERNEL_UMMA_ROWPAIR)
             if (encode_map_a(net, net->blocks[i], net->blocks[i - 1].d_out)) return 1;
     Block &lastb = net->blocks.back();
     if (lastb.out_bf16) return fail("internal: last block stored as bf16");
@@ -839,13 +945,32 @@ int dnnb_net_block_output(dnnb_net *net, int block, float *host_out) {
     return 0;
 }
 
+int dnnb_net_debug_prepool(dnnb_net *net, int block, float *host_out) {
+    if (check_net(net, true)) return 1;
+    if (block < 0 || block >= (int)net->blocks.size() || !host_out) return fail("bad block index or buffer");
+    Block &b = net->blocks[block];
+    if (!b.pool_fused || b.family == DNNB_KERNEL_SIMT) return fail("block %d has no tcgen05-fused pool", block);
+    DeviceGuard g(net->device);
+    const size_t n = (size_t)net->B * b.ch * b.cw * b.oc;
+    DevBuf tmp;
+    if (tmp.alloc(n * 4)) return 1;
+    const void *in = block == 0 ? (net->d_in_cast ? net->d_in_cast : (const void *)net->d_in) : net->blocks[block - 1].d_out;
+    CK(cudaStreamSynchronize(net->stream));
+    if (run_block(net, b, in, nullptr, net->stream, tmp.f())) return 1;
+    CK(cudaStreamSynchronize(net->stream));
+    CK(cudaMemcpy(host_out, tmp.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
     if (check_net(net, true)) return 1;
     if (block < 0 || block >= (int)net->blocks.size() || !info) return fail("bad block index or buffer");
     const Block &b = net->blocks[block];
     info[0] = b.family; info[1] = b.oh; info[2] = b.ow; info[3] = b.oc;
     info[4] = b.pool_fused ? 1 : 0;
-    info[5] = b.bn; info[6] = b.swz; info[7] = b.umma ? b.umma->stages : 0; info[8] = b.grid;
+    info[5] = b.bn; info[6] = b.swz;
+    info[7] = b.umma ? b.umma->stages : b.rowpair ? b.rowpair->stages : b.family == DNNB_KERNEL_UMMA_CONV0 ? conv0::kStages : 0;
+    info[8] = b.grid;
     info[9] = b.pool_separate ? 1 : 0;
     info[10] = b.out_bf16 ? 2 : 4;
     info[11] = 1 + (b.pool_separate ? 1 : 0);

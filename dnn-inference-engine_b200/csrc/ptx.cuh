@@ -171,6 +171,14 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_
     return d;
 }
 
+// The same descriptor split in two 32-bit words, so that issue loops only add constants to the
+// low word: lo = (start >> 4) | LBO(1) << 16, hi = SBO >> 4 | version << 14 | layout << 29.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t swz) {
+    return ((8u * swz) >> 4) | (1u << 14) | ((swz == 128 ? 2u : (swz == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // Instruction descriptor (upper 32 bits of the "idesc" operand): fp32 accumulate, A and B
 // K-major, M = 128, N = n.  fmt: 1 = BF16, 2 = TF32.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t n, uint32_t m = 128) {

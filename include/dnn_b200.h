@@ -42,6 +42,7 @@ typedef struct dnnb_net dnnb_net; /* opaque network handle */
 #define DNNB_KERNEL_SIMT 0      /* CUDA-core direct convolution                 */
 #define DNNB_KERNEL_UMMA_TILED 1 /* tcgen05 implicit GEMM, TMA tiled boxes, fused 2x2/2 pool */
 #define DNNB_KERNEL_UMMA_IM2COL 2 /* tcgen05 implicit GEMM, TMA im2col loads     */
+#define DNNB_KERNEL_UMMA_ROWPAIR 4 /* tcgen05, patch-resident row-pair tiles, resident weights, fused pool */
 #define DNNB_KERNEL_UMMA_CONV0 3 /* tcgen05, 3-channel first layer from the raw image, patch-resident, fused pool */
 
 const char *dnnb_last_error(void);
@@ -113,6 +114,13 @@ int dnnb_net_sync(dnnb_net *net);
 /* Debug / layer-wise comparison: copies block `block`'s output (after its pool, if any) to
  * host as float32 [b,h,w,c]; shape via dnnb_net_block_info. */
 int dnnb_net_block_output(dnnb_net *net, int block, float *host_out);
+
+/* Debug, operator-local pool check: re-runs block `block` (which must have its 2x2/2 pool fused in
+ * a tcgen05 epilogue) on the input it saw in the last forward, this time also dumping the
+ * activations the fused pool reduces -- [b, conv_h, conv_w, c] float32, after scale/shift,
+ * LeakyReLU and storage rounding -- which otherwise never leave the SM.  The block's pooled
+ * output is rewritten with identical values. */
+int dnnb_net_debug_prepool(dnnb_net *net, int block, float *host_out);
 
 /* info[0..11] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
  * epilogue), BN tile, swizzle bytes, stages, grid, separate-pool-kernel(0/1), elem bytes of the

@@ -148,6 +148,8 @@ def test_each_yolo_block_fused_vs_oracle(oracle_libs, layer, batch, precision):
     print("layer %d %s: kernel=%s err=%.3g" % (layer, precision, info["kernel"], err))
     if layer == 0:
         assert info["kernel"] == "umma_conv0" and info["pool_fused"]   # 3 channels: patch-resident kernel
+    elif layer <= 2:
+        assert info["kernel"] == "umma_rowpair" and info["pool_fused"]
     elif layer <= 4:
         assert info["kernel"] == "umma_tiled_pool" and info["pool_fused"]
     else:
@@ -157,21 +159,31 @@ def test_each_yolo_block_fused_vs_oracle(oracle_libs, layer, batch, precision):
     net.close()
 
 
-@pytest.mark.parametrize("layer,batch", [(1, 1), (3, 8), (4, 5)])
-def test_fused_pool_picks_the_reference_maximum(oracle_libs, layer, batch):
-    """Operator-local max-pool identity: given the SAME pre-pool tensor (the fused kernel's own
-    activations, obtained from the identical block without its pool), the fused 2x2/2 pool must
-    return exactly what the oracle's max_pool2d returns, hence the same window index."""
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("layer,batch", [(0, 1), (1, 1), (2, 2), (3, 8), (4, 5)])
+def test_fused_pool_picks_the_reference_maximum(oracle_libs, layer, batch, precision):
+    """Operator-local max-pool identity.  The fused epilogue is asked to also dump the very
+    activations it pools (they normally never leave the SM); the oracle's max_pool2d applied to
+    that dump must reproduce the fused output bit for bit, hence the same window index."""
     w = make_weights(30 + layer)[layer]
     x = np.random.default_rng(50 + layer).standard_normal((batch, HW[layer], HW[layer], CHANNELS[layer])).astype(np.float32)
-    pooled = _lib.Net(x.shape, [_layer_spec(layer, w)], precision="tf32").forward(x)
-    prepool = _lib.Net(x.shape, [_layer_spec(layer, w, pool=False)], precision="tf32").forward(x)
+    nxt = make_weights(31)[layer + 1]                       # a second block so block 0 stores its real dtype
+    net = _lib.Net(x.shape, [_layer_spec(layer, w), _layer_spec(layer + 1, nxt)], precision=precision)
+    net.forward(x)
+    assert net.block_info(0)["pool_fused"]
+    pooled = net.block_output(0)
+    prepool = net.debug_prepool(0, (HW[layer], HW[layer]))
+    np.testing.assert_array_equal(net.block_output(0), pooled)        # the debug re-run changes nothing
     ref, ref_idx = chain.pool_argmax(prepool, 2, 2)
     np.testing.assert_array_equal(pooled, ref)
     b, h, w_, c = prepool.shape
     win = prepool.reshape(b, h // 2, 2, w_ // 2, 2, c).transpose(0, 1, 3, 5, 2, 4).reshape(b, h // 2, w_ // 2, c, 4)
     got_idx = (win == pooled[..., None]).argmax(-1)       # first position holding the returned value
     np.testing.assert_array_equal(got_idx, ref_idx)
+    # and the dumped activations are the block's real ones: they match the oracle's pre-pool tensor
+    oracle_pre = _oracle_block(layer, w, x, pool=False)
+    assert normalised_error(prepool, oracle_pre) < (2e-3 if precision == "tf32" else 1.2e-2)
+    net.close()
 
 
 # ------------------------------------------------------------------------------- end to end
@@ -198,7 +210,7 @@ def test_yolo_batch1_against_reference_golden(precision, wseed, iseed):
     print("yolo b1 %s w%d: err=%.3g plan=%s" % (precision, wseed, err, plan))
     assert err < TOL[precision]
     if precision != "fp32":
-        assert plan == ["umma_conv0"] + ["umma_tiled_pool"] * 4 + ["umma_im2col"] * 4
+        assert plan == ["umma_conv0"] + ["umma_rowpair"] * 2 + ["umma_tiled_pool"] * 2 + ["umma_im2col"] * 4
     # argmax of detections: identical except on genuine near-ties
     a, r = _class_argmax(out), _class_argmax(ref)
     cls_ref = ref.reshape(1, 13, 13, 5, 25)[..., 5:]
