@@ -63,13 +63,14 @@ _sig("dnnb_net_destroy", c_void_p)
 _sig("dnnb_host_alloc", c_size_t, ctypes.POINTER(c_void_p))
 _sig("dnnb_host_free", c_void_p)
 _sig("dnnb_measure_mma_peak", c_int, c_int, FP)
+_sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 
 EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
            "dnnb_net_forward_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
-           "dnnb_host_free", "dnnb_measure_mma_peak"]
+           "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained"]
 
 
 def check(status):
@@ -219,7 +220,11 @@ class Net:
         return n.value
 
 
-def measure_mma_peak(precision="tf32", device=0):
+def measure_mma_peak(precision="tf32", device=0, seconds=0.0):
+    """tcgen05 issue-loop throughput in TFLOP/s: burst (seconds == 0) or sustained over `seconds`."""
     t = c_float(0)
-    check(lib.dnnb_measure_mma_peak(device, PRECISIONS[precision], ctypes.byref(t)))
+    if seconds > 0:
+        check(lib.dnnb_measure_mma_peak_sustained(device, PRECISIONS[precision], float(seconds), ctypes.byref(t)))
+    else:
+        check(lib.dnnb_measure_mma_peak(device, PRECISIONS[precision], ctypes.byref(t)))
     return t.value

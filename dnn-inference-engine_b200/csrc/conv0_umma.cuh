@@ -56,6 +56,8 @@ struct Params {
     int col_tiles;       // ceil(W / 128)
     int num_tiles;       // B * (H/2) * col_tiles
     int leaky, round_tf32;
+    int pool_first;      // every scale[c] > 0: scale/shift, LeakyReLU and rounding are then monotone, so the
+                         // epilogue pools the raw accumulators and activates one value instead of four
     float *prepool;      // debug: also dump the pre-pool activations [B,H,W,16] fp32
 };
 
@@ -103,6 +105,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ patch producers
+        // 136 groups of 4 pixels per patch; lane handles groups lane, lane+32, ... (5 rounds).  The
+        // group -> (patch row, column group) split does not depend on the tile: hoist it.
+        int g_row[5], g_src[5], g_dst[5], g_px[5];
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int g = lane + 32 * it;
+            const int r = g / kGroups, gx = g - r * kGroups;
+            g_row[it] = g < 4 * kGroups ? r : 1 << 20;              // invalid groups fail the row test below
+            g_px[it] = 4 * gx - 4;
+            g_src[it] = (r * p.W + 4 * gx - 4) * 3;
+            g_dst[it] = r * kPatchRowBytes + gx * 64;
+        }
         for (int t = warp; t < my_tiles; t += kProducerWarps) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int ct = tile % p.col_tiles;
@@ -111,30 +125,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             const int w0 = ct * 128;
             const int stage = t % kStages;
             const uint32_t phase = (t / kStages) & 1;
-            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            uint8_t *patch = s_patch + stage * kPatchBytes;
-            const float *img = p.in + (size_t)n * p.H * p.W * 3;
-            // 136 groups of 4 pixels; lane handles groups lane, lane+32, ... (5 rounds, loads first)
+            // pointer to pixel (row 2j-1, column w0) of image n; only dereferenced where in range
+            const float *base = p.in + ((size_t)n * p.H * p.W + (long long)(2 * j - 1) * p.W + w0) * 3;
             float4 v[5][3];
 #pragma unroll
             for (int it = 0; it < 5; ++it) {
-                const int g = lane + 32 * it;
-                const int r = g / kGroups, gx = g - r * kGroups;
-                const int iy = 2 * j - 1 + r, px = w0 - 4 + 4 * gx;
-                const bool ok = g < 4 * kGroups && iy >= 0 && iy < p.H && px >= 0 && px < p.W;
+                const bool ok = (unsigned)(2 * j - 1 + g_row[it]) < (unsigned)p.H && (unsigned)(w0 + g_px[it]) < (unsigned)p.W;
                 if (ok) {
-                    const float4 *src = reinterpret_cast<const float4 *>(img + ((size_t)iy * p.W + px) * 3);
+                    const float4 *src = reinterpret_cast<const float4 *>(base + g_src[it]);
                     v[it][0] = __ldg(src); v[it][1] = __ldg(src + 1); v[it][2] = __ldg(src + 2);
                 } else {
                     v[it][0] = v[it][1] = v[it][2] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);     // loads are already in flight
+            uint8_t *patch = s_patch + stage * kPatchBytes;
 #pragma unroll
             for (int it = 0; it < 5; ++it) {
-                const int g = lane + 32 * it;
-                if (g < 4 * kGroups) {
-                    const int r = g / kGroups, gx = g - r * kGroups;
-                    uint4 *dst = reinterpret_cast<uint4 *>(patch + r * kPatchRowBytes + gx * 64);
+                if (g_row[it] < 4) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(patch + g_dst[it]);
                     const float f[12] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y,
                                          v[it][1].z, v[it][1].w, v[it][2].x, v[it][2].y, v[it][2].z, v[it][2].w};
 #pragma unroll
@@ -202,6 +211,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
         const int m = quarter * 32 + lane;            // pixel column within the tile
         const int OW = p.W >> 1;
+        const bool odd = lane & 1;
+        float sc8[8], sh8[8];                          // scale/shift of the 8 channels this lane stores
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { sc8[c] = s_scale[(odd ? 8 : 0) + c]; sh8[c] = s_shift[(odd ? 8 : 0) + c]; }
         for (int t = group; t < my_tiles; t += kEpilogueGroups) {
             const int tile = blockIdx.x + t * gridDim.x;
             const int ct = tile % p.col_tiles;
@@ -229,23 +242,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                         }
                     }
                 }
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
-                    float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
-                    if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                    float mx = fmaxf(a, b);                      // vertical max: rows 2j, 2j+1
-                    if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
-                    else if (p.round_tf32) mx = ptx::round_tf32(mx);
-                    v[c] = mx;                                   // rounding is monotone: max then round == round then max
-                }
-                const bool odd = lane & 1;
                 float r8[8];
+                if (p.pool_first) {
+                    // all scales positive: pool the raw accumulators (2 rows here, 2 columns by shuffle),
+                    // then scale/shift + LeakyReLU + rounding on the 8 channels this lane stores
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float keep = odd ? v[8 + c] : v[c];
-                    const float send = odd ? v[c] : v[8 + c];
-                    r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));   // horizontal max: columns w, w^1
+                    for (int c = 0; c < 8; ++c) {
+                        const float lo = fmaxf(__uint_as_float(raw[c]), __uint_as_float(raw[16 + c]));
+                        const float hi = fmaxf(__uint_as_float(raw[8 + c]), __uint_as_float(raw[24 + c]));
+                        const float keep = odd ? hi : lo;
+                        const float send = odd ? lo : hi;
+                        float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        y = fmaf(y, sc8[c], sh8[c]);
+                        if (p.leaky) y = fmaxf(y, 0.1f * y);
+                        if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                        else if (p.round_tf32) y = ptx::round_tf32(y);
+                        r8[c] = y;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
+                        float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
+                        if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                        float mx = fmaxf(a, b);                      // vertical max: rows 2j, 2j+1
+                        if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
+                        else if (p.round_tf32) mx = ptx::round_tf32(mx);
+                        v[c] = mx;                                   // rounding is monotone: max then round == round then max
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float keep = odd ? v[8 + c] : v[c];
+                        const float send = odd ? v[c] : v[8 + c];
+                        r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));   // horizontal max: columns w, w^1
+                    }
                 }
                 if (w < p.W) {
                     const size_t pix = ((size_t)n * rows2 + j) * OW + (w >> 1);

@@ -38,6 +38,7 @@ struct Params {
     const float *shift;   // [OC]
     void *out;            // [B, H/2, W/2, OC]
     int leaky, round_tf32;
+    int pool_first;       // every scale[c] > 0: pool the raw accumulators, then activate one value instead of four
     float *prepool;       // debug: also dump the pre-pool activations [B,H,W,OC] fp32
 };
 
@@ -206,23 +207,46 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             p.prepool[(((size_t)n * p.H + 2 * j + 1) * p.W + w) * OC + c0 + c] = b;
                         }
                     }
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
-                        float a = fmaf(__uint_as_float(top[c]), sc, sh);
-                        float b = fmaf(__uint_as_float(bot[c]), sc, sh);
-                        if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                        float mx = fmaxf(a, b);                  // vertical max; rounding is monotone, so round after
-                        if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
-                        else if (p.round_tf32) mx = ptx::round_tf32(mx);
-                        v[c] = mx;
-                    }
                     float r8[8];
+                    if (p.pool_first) {
+                        // all scales positive: max over the 2x2 window of raw accumulators first
+                        const float4 sca = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0));
+                        const float4 scb = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0) + 4);
+                        const float4 sha = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0));
+                        const float4 shb = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0) + 4);
+                        const float sc8[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+                        const float sh8[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float keep = odd ? v[8 + c] : v[c];
-                        const float send = odd ? v[c] : v[8 + c];
-                        r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        for (int c = 0; c < 8; ++c) {
+                            const float lo = fmaxf(__uint_as_float(top[c]), __uint_as_float(bot[c]));
+                            const float hi = fmaxf(__uint_as_float(top[8 + c]), __uint_as_float(bot[8 + c]));
+                            const float keep = odd ? hi : lo;
+                            const float send = odd ? lo : hi;
+                            float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                            y = fmaf(y, sc8[c], sh8[c]);
+                            if (p.leaky) y = fmaxf(y, 0.1f * y);
+                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                            else if (p.round_tf32) y = ptx::round_tf32(y);
+                            r8[c] = y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
+                            float a = fmaf(__uint_as_float(top[c]), sc, sh);
+                            float b = fmaf(__uint_as_float(bot[c]), sc, sh);
+                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                            float mx = fmaxf(a, b);                  // vertical max; rounding is monotone, so round after
+                            if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
+                            else if (p.round_tf32) mx = ptx::round_tf32(mx);
+                            v[c] = mx;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float keep = odd ? v[8 + c] : v[c];
+                            const float send = odd ? v[c] : v[8 + c];
+                            r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        }
                     }
                     if (w < p.W) {
                         const size_t off = pix * OC + c0 + (odd ? 8 : 0);

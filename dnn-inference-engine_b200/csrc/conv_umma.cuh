@@ -51,27 +51,36 @@ struct Params {
     float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
 };
 
-template <int BN, int SWZ, int KBS>
+// MT = M tiles (of 128 rows) per CTA tile that share every B tile: MT = 2 turns the CTA tile
+// into 256 x BN, a third less L2->SMEM traffic per flop, at the price of a single accumulator
+// stage when 2 * BN = 512 (the epilogue then no longer overlaps the next tile's MMAs; with the
+// long K loops of the 13x13 layers that costs ~2%).
+template <int BN, int SWZ, int KBS, int MT = 1>
 struct Cfg {
     static constexpr int A_TILE = kBM * SWZ;
     static constexpr int B_TILE = BN * SWZ;
-    static constexpr int STAGE_BYTES = KBS * (A_TILE + B_TILE);
+    static constexpr int STAGE_BYTES = KBS * (MT * A_TILE + B_TILE);
     static constexpr int TAIL_BYTES = 1024 /*barriers+tmem slot*/ + 2 * 1024 * 4 /*scale, shift*/;
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - TAIL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES + 1024;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int ACC_COLS = MT * BN;
+    static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
+    static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS < 32 ? 32 : ACC_STAGES * ACC_COLS;
     static_assert(STAGES >= 2, "pipeline needs at least two stages");
-    static_assert(TMEM_COLS <= 512, "two accumulator stages must fit TMEM");
+    static_assert(ACC_COLS <= 512, "accumulators must fit TMEM");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocations are powers of two");
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const Params p) {
-    using C = Cfg<BN, SWZ, KBS>;
+    using C = Cfg<BN, SWZ, KBS, MT>;
     constexpr int STAGES = C::STAGES;
+    constexpr int ACC = C::ACC_STAGES;
+    static_assert(MT == 1 || IM2COL, "multi-M tiles are implemented for the im2col mode");
     constexpr int ES = BF16 ? 2 : 4;
     constexpr int BKC = SWZ / ES;            // channels per K-block
     constexpr int MMA_PER_KB = SWZ / 32;     // each MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
@@ -104,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::mbar_init(bar_full + 8 * s, 1);
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ACC; ++s) {
             ptx::mbar_init(bar_tfull + 8 * s, 1);
             ptx::mbar_init(bar_tempty + 8 * s, 128);
         }
@@ -128,35 +137,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int m_tile = tile / p.num_n_tiles;
-                int w0, h0, n0;
+                int w0[MT], h0[MT], n0[MT];
                 if constexpr (IM2COL) {
-                    const int m0 = m_tile * kBM;
-                    n0 = m0 / (p.H * p.W);
-                    const int rem = m0 - n0 * (p.H * p.W);
-                    h0 = rem / p.W;
-                    w0 = rem - h0 * p.W;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const int m0 = (m_tile * MT + i) * kBM;
+                        n0[i] = m0 / (p.H * p.W);
+                        const int rem = m0 - n0[i] * (p.H * p.W);
+                        h0[i] = rem / p.W;
+                        w0[i] = rem - h0[i] * p.W;
+                    }
                 } else {
-                    w0 = (m_tile % p.tiles_w) * p.tw;
-                    h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                    n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                    w0[0] = (m_tile % p.tiles_w) * p.tw;
+                    h0[0] = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                    n0[0] = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
                 }
                 for (int ks = 0; ks < num_kstages; ++ks) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     ptx::mbar_expect_tx(full, C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-                    const uint32_t sb = sa + KBS * C::A_TILE;
+                    const uint32_t sb = sa + KBS * MT * C::A_TILE;
 #pragma unroll
                     for (int j = 0; j < KBS; ++j) {
                         const int kb = ks * KBS + j;
                         const int tap = kb / p.c_chunks;
                         const int cc = kb - tap * p.c_chunks;
                         const int di = tap / p.KW, dj = tap - di * p.KW;
-                        if constexpr (IM2COL)
-                            ptx::tma_load_im2col_4d(sa + j * C::A_TILE, &map_a, full, cc * BKC, w0 - p.PL, h0 - p.PT, n0,
-                                                    (uint16_t)dj, (uint16_t)di);
-                        else
-                            ptx::tma_load_4d(sa + j * C::A_TILE, &map_a, full, cc * BKC, w0 + dj - p.PL, h0 + di - p.PT, n0);
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) {
+                            const uint32_t dst = sa + (j * MT + i) * C::A_TILE;
+                            if constexpr (IM2COL)
+                                ptx::tma_load_im2col_4d(dst, &map_a, full, cc * BKC, w0[i] - p.PL, h0[i] - p.PT, n0[i],
+                                                        (uint16_t)dj, (uint16_t)di);
+                            else
+                                ptx::tma_load_4d(dst, &map_a, full, cc * BKC, w0[i] + dj - p.PL, h0[i] + di - p.PT, n0[i]);
+                        }
                         ptx::tma_load_3d(sb + j * C::B_TILE, &map_b, full, cc * BKC, n_tile * BN, tap);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -167,27 +183,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1u : 2u, BN);
+            constexpr uint32_t HI = ptx::umma_desc_hi(SWZ);
             int stage = 0;
             uint32_t phase = 0;
             int local = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-                const int acc = local & 1;
-                const uint32_t acc_phase = (local >> 1) & 1;
+                const int acc = local % ACC;
+                const uint32_t acc_phase = (local / ACC) & 1;
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
                 for (int ks = 0; ks < num_kstages; ++ks) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-                    const uint32_t sb = sa + KBS * C::A_TILE;
+                    const uint32_t a_lo = ptx::umma_desc_lo(smem_base + stage * C::STAGE_BYTES);
+                    const uint32_t b_lo = a_lo + ((KBS * MT * C::A_TILE) >> 4);
 #pragma unroll
                     for (int j = 0; j < KBS; ++j) {
-                        const uint64_t da = ptx::umma_desc_kmajor(sa + j * C::A_TILE, SWZ);
-                        const uint64_t db = ptx::umma_desc_kmajor(sb + j * C::B_TILE, SWZ);
 #pragma unroll
-                        for (int k = 0; k < MMA_PER_KB; ++k)
-                            ptx::umma<BF16>(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | j | k) != 0 ? 1u : 0u);
+                        for (int i = 0; i < MT; ++i) {
+#pragma unroll
+                            for (int k = 0; k < MMA_PER_KB; ++k)
+                                ptx::umma<BF16>(d_tmem + i * BN,
+                                                ptx::umma_desc_join(a_lo + (((j * MT + i) * C::A_TILE + 32 * k) >> 4), HI),
+                                                ptx::umma_desc_join(b_lo + ((j * C::B_TILE + 32 * k) >> 4), HI), idesc,
+                                                (ks | j | k) != 0 ? 1u : 0u);
+                        }
                     }
                     ptx::umma_commit(bar_empty + 8 * stage);   // smem slot free once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -201,16 +222,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int row = quarter * 32 + lane;           // tile row = output pixel slot
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-            const int acc = local & 1;
-            const uint32_t acc_phase = (local >> 1) & 1;
+            const int acc = local % ACC;
+            const uint32_t acc_phase = (local / ACC) & 1;
             const int n_tile = tile % p.num_n_tiles;
             const int m_tile = tile / p.num_n_tiles;
+            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            ptx::tc_fence_after();
 
+#pragma unroll 1
+            for (int mi = 0; mi < MT; ++mi) {
             bool valid;
             size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
             size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
             if constexpr (IM2COL) {
-                const int m = m_tile * kBM + row;
+                const int m = (m_tile * MT + mi) * kBM + row;
                 valid = m < p.M_total;
                 out_pix = (size_t)m;
             } else {
@@ -227,13 +252,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 pre_pix = ((size_t)n * p.H + h) * p.W + w;
             }
 
-            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            ptx::tc_fence_after();
-
 #pragma unroll 1
             for (int chunk = 0; chunk < BN / 32; ++chunk) {
                 uint32_t raw[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 32, raw);
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
                 ptx::tmem_ld_wait();
                 const int col0 = n_tile * BN + chunk * 32;
                 float v[32];
@@ -345,6 +367,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
+            }   // mi
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
         }

@@ -110,6 +110,19 @@ void out_pads(int in_size, int k, int s, int same, int *o, int *pf, int *pb) {
     }
 }
 
+// opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel, device)
+template <typename K>
+cudaError_t set_smem_once(K kern, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 kernel instantiations and their dispatch table
 typedef cudaError_t (*UmmaLauncher)(const CUtensorMap &, const CUtensorMap &, const umma_conv::Params &, int grid,
@@ -118,6 +131,7 @@ struct UmmaKey {
     bool bf16, out_bf16;
     int bn, swz, kbs;
     bool im2col, pool;
+    int mt;   // 128-row M tiles per CTA tile
 };
 struct UmmaEntry {
     UmmaKey key;
@@ -125,28 +139,22 @@ struct UmmaEntry {
     int stages, smem;
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT>
 cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
                         cudaStream_t st) {
-    using C = umma_conv::Cfg<BN, SWZ, KBS>;
-    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL>;
-    static bool configured = false;   // per process; every device of one box is the same part
-    static int configured_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured || configured_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-        configured_dev = dev;
-    }
+    using C = umma_conv::Cfg<BN, SWZ, KBS, MT>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT>;
+    static bool done[64] = {};
+    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
+    if (e != cudaSuccess) return e;
     kern<<<grid, umma_conv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);
     return cudaGetLastError();
 }
 
-#define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL)                                      \
-    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL>, \
-     umma_conv::Cfg<BN, SWZ, KBS>::STAGES, umma_conv::Cfg<BN, SWZ, KBS>::SMEM_BYTES}
+#define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                          \
+    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>,     \
+     umma_conv::Cfg<BN, SWZ, KBS, MT>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, MT>::SMEM_BYTES}
+#define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
 
 const UmmaEntry g_umma_table[] = {
     // TF32 operands (fp32 storage in and out)
@@ -176,12 +184,16 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(true, false, 128, 128, 1, true, false),
     UMMA_ENTRY(true, false, 64, 64, 3, true, false),
     UMMA_ENTRY(true, false, 32, 32, 3, true, false),
+    // 256 x 256 CTA tiles (two M tiles share each weight tile) for the long-K 13x13 layers
+    UMMA_ENTRY_MT(false, false, 256, 128, 1, true, false, 2),
+    UMMA_ENTRY_MT(true, true, 256, 128, 1, true, false, 2),
+    UMMA_ENTRY_MT(true, false, 256, 128, 1, true, false, 2),
 };
 
 const UmmaEntry *find_umma(const UmmaKey &k) {
     for (const UmmaEntry &e : g_umma_table)
         if (e.key.bf16 == k.bf16 && e.key.out_bf16 == k.out_bf16 && e.key.bn == k.bn && e.key.swz == k.swz &&
-            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool)
+            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool && e.key.mt == k.mt)
             return &e;
     return nullptr;
 }
@@ -202,7 +214,8 @@ cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const r
                            cudaStream_t st) {
     using C = rowpair::Cfg<OC, SWZ>;
     auto kern = rowpair::conv_rowpair_kernel<BF16, OUT_BF16, OC, SWZ>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    static bool done[64] = {};
+    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
     kern<<<grid, rowpair::kThreads, C::SMEM_BYTES, st>>>(ma, mw, p);
     return cudaGetLastError();
@@ -342,6 +355,14 @@ int encode_map_b(Block &b) {
     return 0;
 }
 
+// scale/shift + LeakyReLU + rounding is monotone non-decreasing when scale > 0: pooling may then
+// run on the raw accumulators (f(max(a, b)) == max(f(a), f(b)) exactly)
+bool all_scales_positive(const Block &b) {
+    for (float v : b.scale)
+        if (!(v > 0.f)) return false;
+    return true;
+}
+
 // Decide how block `i` runs.  in_bf16: storage type of its input.
 void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     Block &b = net->blocks[i];
@@ -368,6 +389,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         c.col_tiles = (b.iw + 127) / 128;
         c.num_tiles = net->B * (b.ih / 2) * c.col_tiles;
         c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
+        c.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
         b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
         b.bn = 16; b.swz = 0;
         return;
@@ -391,6 +413,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
             r.col_tiles = (b.iw + 127) / 128;
             r.num_tiles = net->B * (b.ih / 2) * r.col_tiles;
             r.leaky = b.leaky; r.round_tf32 = b.round_tf32;
+            r.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
             b.grid = r.num_tiles < net->num_sms ? r.num_tiles : net->num_sms;
             return;
         }
@@ -416,8 +439,17 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 nb = 128 / (tw * th);
                 fuse = tw >= 2 && th >= 2;
             }
-            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse};
+            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1};
             const UmmaEntry *e = find_umma(key);
+            int mt = 1;
+            if (e && !fuse && !getenv("DNNB_NO_MT2")) {
+                // enough work for 256-row CTA tiles?  (two waves of them, or they just idle SMs)
+                const long tiles2 = ((long)net->B * b.ih * b.iw + 255) / 256 * (ocp / bn);
+                UmmaKey key2 = key;
+                key2.mt = 2;
+                const UmmaEntry *e2 = tiles2 >= 2L * net->num_sms ? find_umma(key2) : nullptr;
+                if (e2) { e = e2; mt = 2; }
+            }
             if (e) {
                 b.umma = e;
                 b.family = fuse ? DNNB_KERNEL_UMMA_TILED : DNNB_KERNEL_UMMA_IM2COL;
@@ -438,7 +470,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 } else {
                     p.tw = p.th = p.nb = 1;
                     p.M_total = net->B * b.ih * b.iw;
-                    p.num_m_tiles = (p.M_total + umma_conv::kBM - 1) / umma_conv::kBM;
+                    p.num_m_tiles = (p.M_total + umma_conv::kBM * mt - 1) / (umma_conv::kBM * mt);
                     p.OH = b.ih; p.OW = b.iw;
                 }
                 p.leaky = b.leaky;
@@ -457,7 +489,8 @@ template <bool BF16, bool OUT_BF16>
 cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
     auto kern = conv0::conv0_kernel<BF16, OUT_BF16>;
     const int smem = conv0::kSmemBytes + 128;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static bool done[64] = {};
+    cudaError_t e = set_smem_once(kern, smem, done);
     if (e != cudaSuccess) return e;
     kern<<<grid, conv0::kThreads, smem, st>>>(p);
     return cudaGetLastError();
@@ -487,6 +520,12 @@ int ew_grid(size_t n, int num_sms) {
 
 cudaError_t run_pool(const simt::PoolParams &p, bool bf16, int num_sms, cudaStream_t st) {
     const size_t n = (size_t)p.B * p.OH * p.OW * p.C;
+    if (p.C % 4 == 0) {
+        const int grid = ew_grid(n / 4, num_sms);
+        if (bf16) simt::maxpool_vec4_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+        else simt::maxpool_vec4_kernel<float><<<grid, 256, 0, st>>>(p);
+        return cudaGetLastError();
+    }
     const int grid = ew_grid(n, num_sms);
     if (bf16) simt::maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
     else simt::maxpool_kernel<float><<<grid, 256, 0, st>>>(p);
@@ -1074,7 +1113,9 @@ int dnnb_host_free(void *p) {
     return 0;
 }
 
-int dnnb_measure_mma_peak(int device, int precision, float *tflops) {
+// seconds <= 0: burst (best of 5 short launches); otherwise back-to-back launches for `seconds`
+// and the mean rate of the second half (the clock the part settles at under its power cap)
+static int measure_mma_peak_impl(int device, int precision, float seconds, float *tflops) {
     if (!tflops) return fail("null argument");
     if (precision != DNNB_TF32 && precision != DNNB_BF16) return fail("precision must be TF32 or BF16");
     DeviceGuard g(device);
@@ -1092,27 +1133,55 @@ int dnnb_measure_mma_peak(int device, int precision, float *tflops) {
         }
         return cudaGetLastError();
     };
+    const double k_per_mma = precision == DNNB_BF16 ? 16.0 : 8.0;
+    const double flops = (double)sms * iters * 4.0 * 2.0 * 128.0 * 256.0 * k_per_mma;
     CK(run(256));
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
-        CK(cudaEventRecord(e0));
-        CK(run(iters));
-        CK(cudaEventRecord(e1));
-        CK(cudaEventSynchronize(e1));
-        float t = 0.f;
-        CK(cudaEventElapsedTime(&t, e0, e1));
-        if (t < best) best = t;
+    if (seconds <= 0.f) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(e0));
+            CK(run(iters));
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (t < best) best = t;
+        }
+        *tflops = (float)(flops / (best * 1e-3) / 1e12);
+    } else {
+        std::vector<float> times;
+        double elapsed = 0.0;
+        while (elapsed < seconds * 1e3 && times.size() < 100000) {
+            CK(cudaEventRecord(e0));
+            for (int k = 0; k < 8; ++k) CK(run(iters));
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            times.push_back(t / 8.f);
+            elapsed += t;
+        }
+        double sum = 0.0;
+        size_t n = 0;
+        for (size_t i = times.size() / 2; i < times.size(); ++i) { sum += times[i]; ++n; }
+        *tflops = (float)(flops / (sum / n * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    const double k_per_mma = precision == DNNB_BF16 ? 16.0 : 8.0;
-    const double flops = (double)sms * iters * 4.0 * 2.0 * 128.0 * 256.0 * k_per_mma;
-    *tflops = (float)(flops / (best * 1e-3) / 1e12);
     return 0;
+}
+
+int dnnb_measure_mma_peak(int device, int precision, float *tflops) {
+    return measure_mma_peak_impl(device, precision, 0.f, tflops);
+}
+
+int dnnb_measure_mma_peak_sustained(int device, int precision, float seconds, float *tflops) {
+    if (!(seconds > 0.f) || seconds > 30.f) return fail("seconds must be in (0, 30]");
+    return measure_mma_peak_impl(device, precision, seconds, tflops);
 }
 
 }  // extern "C"
