@@ -17,8 +17,10 @@
 // epilogue thread of lane m therefore holds both rows of pixel column m: the vertical max is
 // thread-local, the horizontal max one shuffle.
 //
-// Warp roles (448 threads): 4 producer warps (each builds whole patches, tile t -> warp t % 4, so
-// four global-load latencies overlap), 2 MMA warps and 2 x 4 epilogue warps (both alternate tiles).
+// Warp roles (576 threads): 8 producer warps (each builds whole patches, tile t -> warp t % 8, so
+// eight global-load latencies overlap: the producers are latency-bound), 2 MMA warps and 2 x 4
+// epilogue warps (both alternate tiles).  A CTA owns a contiguous range of tiles, so every role walks
+// (column tile, row pair, image) incrementally instead of dividing.
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -31,7 +33,7 @@ namespace conv0 {
 // same MMA warp (kStages is a multiple of both warp counts), and every accumulator stage belongs to
 // one MMA warp and one epilogue group.  Each waiter therefore follows its barrier phase by phase; a
 // waiter that could get two phases ahead would see a stale parity as "done".
-constexpr int kProducerWarps = 4;
+constexpr int kProducerWarps = 8;
 constexpr int kMmaWarps = 2;       // tiles alternate between two issuing warps (small, issue-bound MMAs)
 constexpr int kEpilogueGroups = 2;
 constexpr int kThreads = (kProducerWarps + kMmaWarps + 4 * kEpilogueGroups) * 32;
@@ -101,7 +103,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile_begin = (int)blockIdx.x * per_cta;
+    const int my_tiles = max(0, min(p.num_tiles, tile_begin + per_cta) - tile_begin);
+    // tile -> (column tile ct, row pair j, image n), advanced incrementally
+    struct Coord { int ct, j, n; };
+    auto decode = [&](int tile) {
+        Coord c;
+        c.ct = tile % p.col_tiles;
+        c.j = (tile / p.col_tiles) % rows2;
+        c.n = tile / (p.col_tiles * rows2);
+        return c;
+    };
+    auto advance = [&](Coord &c, int steps) {
+        c.ct += steps;
+        while (c.ct >= p.col_tiles) {
+            c.ct -= p.col_tiles;
+            if (++c.j == rows2) { c.j = 0; ++c.n; }
+        }
+    };
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ patch producers
@@ -117,12 +137,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             g_src[it] = (r * p.W + 4 * gx - 4) * 3;
             g_dst[it] = r * kPatchRowBytes + gx * 64;
         }
-        for (int t = warp; t < my_tiles; t += kProducerWarps) {
-            const int tile = blockIdx.x + t * gridDim.x;
-            const int ct = tile % p.col_tiles;
-            const int j = (tile / p.col_tiles) % rows2;
-            const int n = tile / (p.col_tiles * rows2);
-            const int w0 = ct * 128;
+        Coord tc = decode(tile_begin + warp);
+        for (int t = warp; t < my_tiles; t += kProducerWarps, advance(tc, kProducerWarps)) {
+            const int j = tc.j, n = tc.n;
+            const int w0 = tc.ct * 128;
             const int stage = t % kStages;
             const uint32_t phase = (t / kStages) & 1;
             // pointer to pixel (row 2j-1, column w0) of image n; only dereferenced where in range
@@ -215,11 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         float sc8[8], sh8[8];                          // scale/shift of the 8 channels this lane stores
 #pragma unroll
         for (int c = 0; c < 8; ++c) { sc8[c] = s_scale[(odd ? 8 : 0) + c]; sh8[c] = s_shift[(odd ? 8 : 0) + c]; }
-        for (int t = group; t < my_tiles; t += kEpilogueGroups) {
-            const int tile = blockIdx.x + t * gridDim.x;
-            const int ct = tile % p.col_tiles;
-            const int j = (tile / p.col_tiles) % rows2;
-            const int n = tile / (p.col_tiles * rows2);
+        Coord tc = decode(tile_begin + group);
+        for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
+            const int ct = tc.ct, j = tc.j, n = tc.n;
             const int w = ct * 128 + m;
             const int acc = t % kAccStages;
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / kAccStages) & 1);

@@ -94,7 +94,25 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows2 = p.H >> 1;
-    const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // a CTA owns a contiguous range of tiles; (column tile, row pair, image) advance incrementally
+    const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile_begin = (int)blockIdx.x * per_cta;
+    const int my_tiles = max(0, min(p.num_tiles, tile_begin + per_cta) - tile_begin);
+    struct Coord { int ct, j, n; };
+    auto decode = [&](int tile) {
+        Coord c;
+        c.ct = tile % p.col_tiles;
+        c.j = (tile / p.col_tiles) % rows2;
+        c.n = tile / (p.col_tiles * rows2);
+        return c;
+    };
+    auto advance = [&](Coord &c, int steps) {
+        c.ct += steps;
+        while (c.ct >= p.col_tiles) {
+            c.ct -= p.col_tiles;
+            if (++c.j == rows2) { c.j = 0; ++c.n; }
+        }
+    };
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -116,16 +134,13 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (ptx::elect_one()) {
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);                 // resident weights, once
             for (int dj = 0; dj < 3; ++dj) ptx::tma_load_3d(w_base + dj * C::W_DJ_BYTES, &map_w, bar_w, 0, 0, dj);
-            for (int t = 0; t < my_tiles; ++t) {
-                const int tile = blockIdx.x + t * gridDim.x;
-                const int ct = tile % p.col_tiles;
-                const int j = (tile / p.col_tiles) % rows2;
-                const int n = tile / (p.col_tiles * rows2);
+            Coord tc = decode(tile_begin);
+            for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
                 const int stage = t % STAGES;
                 ptx::mbar_wait(bar_empty + 8 * stage, ((t / STAGES) & 1) ^ 1);
                 ptx::mbar_expect_tx(bar_full + 8 * stage, C::PATCH_RAW);
-                ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, ct * 128 - 1,
-                                 2 * j - 1, n);
+                ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, tc.ct * 128 - 1,
+                                 2 * tc.j - 1, tc.n);
             }
         }
     } else if (warp <= kMmaWarps) {
@@ -176,11 +191,9 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m = quarter * 32 + lane;
         const int OW = p.W >> 1;
         const bool odd = lane & 1;
-        for (int t = group; t < my_tiles; t += 2) {
-            const int tile = blockIdx.x + t * gridDim.x;
-            const int ct = tile % p.col_tiles;
-            const int j = (tile / p.col_tiles) % rows2;
-            const int n = tile / (p.col_tiles * rows2);
+        Coord tc = decode(tile_begin + group);
+        for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
+            const int ct = tc.ct, j = tc.j, n = tc.n;
             const int w = ct * 128 + m;
             const int acc = t % ACC;
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
