@@ -175,7 +175,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    args.out.emit(json.dumps(line))
     return 0
 
 
@@ -200,7 +200,7 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:   # plain `python bench.py --gpus N`: relaunch under torchrun
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                    "--master-addr", "127.0.0.1", "--master-port", "29591", os.path.abspath(__file__)] + sys.argv[1:]
-            return subprocess.call(cmd)
+            return subprocess.call(cmd, stdout=args.out.saved)
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
@@ -354,12 +354,26 @@ def run_b200(args):
                                                  GFLOP_PER_IMAGE[i] * 1e9 * mb / (tensor_peak * 1e12)) for i in range(9))
                                         / (sum(l["ms"] for l in layers) * 1e-3)) if layers else None,
         }
-        print(json.dumps(line), flush=True)
+        args.out.emit(json.dumps(line))
     net.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class StdoutGuard:
+    """Everything but the final JSON line goes to stderr: libraries (NCCL's version banner, for one)
+    write to fd 1 behind Python's back, and the contract is ONE line on stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
 
 
 def main():
@@ -376,6 +390,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images timed for cpu_baseline (about 10-30 s)")
     ap.add_argument("--ref-sample", type=int, default=2, help="images per step of --impl reference")
     args = ap.parse_args()
+    args.out = StdoutGuard()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
