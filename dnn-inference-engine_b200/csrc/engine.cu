@@ -377,8 +377,8 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
 
     // first block straight from the raw 3-channel fp32 image: the patch-resident tcgen05 kernel
     if (i == 0 && !in_bf16 && net->precision != DNNB_FP32 && !force_simt && !getenv("DNNB_NO_CONV0") && b.ic == 3 &&
-        b.oc == 16 && b.kh == 3 && b.kw == 3 && b.same && b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 &&
-        b.iw % 4 == 0) {
+        b.oc == 16 && b.kh == 3 && b.kw == 3 && b.same && b.pool_k == 2 && b.pool_s == 2 &&
+        b.ih % conv0::kTileRows == 0 && b.iw % 4 == 0) {
         b.family = DNNB_KERNEL_UMMA_CONV0;
         b.pool_fused = true;
         b.pool_separate = false;
@@ -387,7 +387,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         c = conv0::Params{};
         c.B = net->B; c.H = b.ih; c.W = b.iw;
         c.col_tiles = (b.iw + 127) / 128;
-        c.num_tiles = net->B * (b.ih / 2) * c.col_tiles;
+        c.num_tiles = net->B * (b.ih / conv0::kTileRows) * c.col_tiles;
         c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
         c.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
         b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
