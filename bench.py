@@ -311,9 +311,9 @@ def run_b200(args):
     layers = None
     tensor_peak = None
     if rank == 0:
+        layer_ms = net.time_blocks(2, 5)                                                   # before the 3 s burn below
         tensor_peak = _lib.measure_mma_peak(args.precision, local_rank)                   # burst: kernels timed alone
         tensor_peak_sustained = _lib.measure_mma_peak(args.precision, local_rank, 3.0)   # under the power cap
-        layer_ms = net.time_blocks(2, 5)
         layers = []
         for i, t in enumerate(layer_ms):
             fl = GFLOP_PER_IMAGE[i] * 1e9 * mb

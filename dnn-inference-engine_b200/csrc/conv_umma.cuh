@@ -55,12 +55,16 @@ struct Params {
 // into 256 x BN, a third less L2->SMEM traffic per flop, at the price of a single accumulator
 // stage when 2 * BN = 512 (the epilogue then no longer overlaps the next tile's MMAs; with the
 // long K loops of the 13x13 layers that costs ~2%).
-template <int BN, int SWZ, int KBS, int MT = 1>
+// STAGE_OUT reserves 4 x 32 rows x BN floats so that a tile whose rows are narrower than a 16-byte
+// multiple (block 8: 125 channels = 500-byte rows) is staged in shared memory and written as one
+// contiguous, coalesced run instead of 4-byte scattered stores.
+template <int BN, int SWZ, int KBS, int MT = 1, bool STAGE_OUT = false>
 struct Cfg {
     static constexpr int A_TILE = kBM * SWZ;
     static constexpr int B_TILE = BN * SWZ;
     static constexpr int STAGE_BYTES = KBS * (MT * A_TILE + B_TILE);
-    static constexpr int TAIL_BYTES = 1024 /*barriers+tmem slot*/ + 2 * 1024 * 4 /*scale, shift*/;
+    static constexpr int OUT_STAGE_BYTES = STAGE_OUT ? kBM * BN * 4 : 0;
+    static constexpr int TAIL_BYTES = 1024 /*barriers+tmem slot*/ + 2 * 1024 * 4 /*scale, shift*/ + OUT_STAGE_BYTES;
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - TAIL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -73,14 +77,14 @@ struct Cfg {
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocations are powers of two");
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1, bool STAGE_OUT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const Params p) {
-    using C = Cfg<BN, SWZ, KBS, MT>;
+    using C = Cfg<BN, SWZ, KBS, MT, STAGE_OUT>;
+    static_assert(!STAGE_OUT || (IM2COL && !POOL && !OUT_BF16 && MT == 1), "staged output: plain fp32 im2col tiles only");
     constexpr int STAGES = C::STAGES;
     constexpr int ACC = C::ACC_STAGES;
-    static_assert(MT == 1 || IM2COL, "multi-M tiles are implemented for the im2col mode");
     constexpr int ES = BF16 ? 2 : 4;
     constexpr int BKC = SWZ / ES;            // channels per K-block
     constexpr int MMA_PER_KB = SWZ / 32;     // each MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
@@ -93,6 +97,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
     float *s_scale = reinterpret_cast<float *>(tail + 1024);
     float *s_shift = s_scale + 1024;
+    float *s_out = s_shift + 1024;       // STAGE_OUT only: [4 warps][32 rows][OC]
 
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t bar_full = ptx::smem_u32(bars);
@@ -148,9 +153,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         w0[i] = rem - h0[i] * p.W;
                     }
                 } else {
-                    w0[0] = (m_tile % p.tiles_w) * p.tw;
-                    h0[0] = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                    n0[0] = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {     // the MT sub-tiles are consecutive groups of nb images
+                        w0[i] = (m_tile % p.tiles_w) * p.tw;
+                        h0[i] = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                        n0[i] = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + i) * p.nb;
+                    }
                 }
                 for (int ks = 0; ks < num_kstages; ++ks) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -241,7 +249,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             } else {
                 const int w0 = (m_tile % p.tiles_w) * p.tw;
                 const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.nb;
+                const int n0 = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + mi) * p.nb;
                 const int wl = row & (p.tw - 1);
                 const int hl = (row >> p.log2_tw) & (p.th - 1);
                 const int nl = row >> (p.log2_tw + p.log2_th);
@@ -351,6 +359,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int j = 0; j < 32; ++j)
                                     if (col0 + j < p.OC) o[j] = __float2bfloat16_rn(v[j]);
                             }
+                        } else if constexpr (STAGE_OUT) {
+                            float *so = s_out + (size_t)(quarter * 32 + lane) * p.OC + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.OC) so[j] = v[j];
                         } else {
                             float *o = static_cast<float *>(p.out) + out_pix * p.OC + col0;
                             if ((p.OC & 3) == 0) {
@@ -367,6 +380,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
+            if constexpr (STAGE_OUT) {
+                // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
+                __syncwarp();
+                const int row0 = m_tile * kBM + quarter * 32;
+                const int rows = min(32, p.M_total - row0);
+                if (rows > 0) {
+                    const int count = rows * p.OC;
+                    const float *src = s_out + (size_t)quarter * 32 * p.OC;
+                    float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
+                    if ((((size_t)quarter * 32 * p.OC) & 3) == 0 && (((size_t)row0 * p.OC) & 3) == 0) {
+                        for (int i = lane * 4; i + 3 < count; i += 128)
+                            *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
+                        for (int i = (count & ~3) + lane; i < count; i += 32) dst[i] = src[i];
+                    } else {
+                        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+                    }
+                }
+                __syncwarp();
+            }
             }   // mi
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
@@ -380,15 +412,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-pipe peak probe: every CTA issues `iters` x (128 x 256 x 32B-of-K) MMAs back to back
-// on resident (zeroed) shared memory, no loads, no epilogue.
+// on resident shared memory, no loads, no epilogue.  `random_data`: fill the operands with
+// pseudo-random values in (-1, 1) instead of zeros -- the power a dense MMA draws, hence the clock
+// the part sustains under its power cap, depends on the data toggling.
 template <bool BF16>
-__global__ void __launch_bounds__(64, 1) mma_peak_kernel(int iters) {
+__global__ void __launch_bounds__(64, 1) mma_peak_kernel(int iters, int random_data) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128;
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
-    for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) {
+        uint32_t word = 0;
+        if (random_data) {
+            uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u + 12345u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            if constexpr (BF16) {
+                // two bf16 in (-1, 1): sign, exponent 0x7e (0.5 .. 1), random mantissa
+                const uint32_t lo = ((h & 0x8000u) | 0x3f00u | (h & 0x7fu));
+                const uint32_t hi = (((h >> 16) & 0x8000u) | 0x3f00u | ((h >> 16) & 0x7fu));
+                word = lo | (hi << 16);
+            } else {
+                word = (h & 0x80000000u) | 0x3f000000u | (h & 0x007fe000u);   // tf32-exact fp32 in (-1, 1)
+            }
+        }
+        reinterpret_cast<uint32_t *>(smem)[i] = word;
+    }
     const uint32_t b = ptx::smem_u32(&bar);
     if (threadIdx.x == 0) { ptx::mbar_init(b, 1); ptx::fence_barrier_init(); }
     if (threadIdx.x < 32) ptx::tmem_alloc(ptx::smem_u32(&slot), 512);

@@ -132,6 +132,7 @@ struct UmmaKey {
     int bn, swz, kbs;
     bool im2col, pool;
     int mt;   // 128-row M tiles per CTA tile
+    bool stage_out;   // output tile staged in smem (rows that are not 16-byte multiples)
 };
 struct UmmaEntry {
     UmmaKey key;
@@ -139,11 +140,11 @@ struct UmmaEntry {
     int stages, smem;
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false>
 cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
                         cudaStream_t st) {
-    using C = umma_conv::Cfg<BN, SWZ, KBS, MT>;
-    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT>;
+    using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
@@ -151,9 +152,12 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
     return cudaGetLastError();
 }
 
-#define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                          \
-    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>,     \
+#define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                              \
+    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT, false}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>,  \
      umma_conv::Cfg<BN, SWZ, KBS, MT>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, MT>::SMEM_BYTES}
+#define UMMA_ENTRY_SO(BF16, BN, SWZ, KBS)                                                                  \
+    {{BF16, false, BN, SWZ, KBS, true, false, 1, true}, &launch_umma<BF16, false, BN, SWZ, KBS, true, false, 1, true>, \
+     umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES}
 #define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
 
 const UmmaEntry g_umma_table[] = {
@@ -188,12 +192,21 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY_MT(false, false, 256, 128, 1, true, false, 2),
     UMMA_ENTRY_MT(true, true, 256, 128, 1, true, false, 2),
     UMMA_ENTRY_MT(true, false, 256, 128, 1, true, false, 2),
+    // the same for the fused-pool spatial tiles (two groups of nb images share each weight tile)
+    UMMA_ENTRY_MT(false, false, 128, 128, 1, false, true, 2),
+    UMMA_ENTRY_MT(false, false, 256, 128, 1, false, true, 2),
+    UMMA_ENTRY_MT(true, true, 128, 128, 1, false, true, 2),
+    UMMA_ENTRY_MT(true, true, 256, 128, 1, false, true, 2),
+    // output staged through smem: the 125-channel head (block 8)
+    UMMA_ENTRY_SO(false, 128, 128, 1),
+    UMMA_ENTRY_SO(true, 128, 128, 1),
 };
 
 const UmmaEntry *find_umma(const UmmaKey &k) {
     for (const UmmaEntry &e : g_umma_table)
         if (e.key.bf16 == k.bf16 && e.key.out_bf16 == k.out_bf16 && e.key.bn == k.bn && e.key.swz == k.swz &&
-            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool && e.key.mt == k.mt)
+            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool && e.key.mt == k.mt &&
+            e.key.stage_out == k.stage_out)
             return &e;
     return nullptr;
 }
@@ -439,15 +452,29 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 nb = 128 / (tw * th);
                 fuse = tw >= 2 && th >= 2;
             }
-            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1};
+            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
             const UmmaEntry *e = find_umma(key);
+            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !getenv("DNNB_NO_STAGE_OUT")) {
+                UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
+                key_so.stage_out = true;
+                const UmmaEntry *e_so = find_umma(key_so);
+                if (e_so) e = e_so;
+            }
             int mt = 1;
-            if (e && !fuse && !getenv("DNNB_NO_MT2")) {
-                // enough work for 256-row CTA tiles?  (two waves of them, or they just idle SMs)
-                const long tiles2 = ((long)net->B * b.ih * b.iw + 255) / 256 * (ocp / bn);
+            if (e && !getenv("DNNB_NO_MT2")) {
+                // 256-row CTA tiles (two M tiles share each weight tile) when there is enough work for
+                // at least two waves of them; DNNB_MT2_MASK (bit i = block i) overrides per block
+                const long m_rows = fuse ? (long)((net->B + nb - 1) / nb) * nb * b.ih * b.iw : (long)net->B * b.ih * b.iw;
+                const long tiles2 = (m_rows + 255) / 256 * (ocp / bn);
+                // measured on B200 (TF32, batch 512): it pays when both accumulator stages survive
+                // (BN <= 128: block 3, 0.43 -> 0.28 ms) or when K is long enough to hide the serialised
+                // epilogue (block 7, K = 9216: 2.09 -> 1.98 ms); a wash or a loss otherwise (blocks 4-6)
+                const long k_total = (long)b.kh * b.kw * b.ic;
+                bool want = tiles2 >= 2L * net->num_sms && (2 * bn <= 256 || k_total >= 8192);
+                if (getenv("DNNB_MT2_MASK")) want = (atoi(getenv("DNNB_MT2_MASK")) >> i) & 1;
                 UmmaKey key2 = key;
                 key2.mt = 2;
-                const UmmaEntry *e2 = tiles2 >= 2L * net->num_sms ? find_umma(key2) : nullptr;
+                const UmmaEntry *e2 = want ? find_umma(key2) : nullptr;
                 if (e2) { e = e2; mt = 2; }
             }
             if (e) {
@@ -465,7 +492,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 if (fuse) {
                     p.tw = tw; p.th = th; p.nb = nb; p.log2_tw = ilog2(tw); p.log2_th = ilog2(th);
                     p.tiles_w = b.iw / tw; p.tiles_h = b.ih / th;
-                    p.num_m_tiles = p.tiles_w * p.tiles_h * ((net->B + nb - 1) / nb);
+                    p.num_m_tiles = p.tiles_w * p.tiles_h * ((net->B + nb * mt - 1) / (nb * mt));
                     p.OH = b.ih / 2; p.OW = b.iw / 2;
                 } else {
                     p.tw = p.th = p.nb = 1;
@@ -520,6 +547,13 @@ int ew_grid(size_t n, int num_sms) {
 
 cudaError_t run_pool(const simt::PoolParams &p, bool bf16, int num_sms, cudaStream_t st) {
     const size_t n = (size_t)p.B * p.OH * p.OW * p.C;
+    if (p.C % 4 == 0 && p.KH == 2 && p.KW == 2 && p.SH == 1 && p.SW == 1 && p.PT == 0 && p.PL == 0 && p.OH == p.IH &&
+        p.OW == p.IW && (long)p.B * p.OH < 2000000000L) {
+        const int threads = p.C / 4 < 256 ? (p.C / 4 + 31) / 32 * 32 : 256;
+        if (bf16) simt::maxpool_2x2s1_kernel<__nv_bfloat16><<<p.B * p.OH, threads, 0, st>>>(p);
+        else simt::maxpool_2x2s1_kernel<float><<<p.B * p.OH, threads, 0, st>>>(p);
+        return cudaGetLastError();
+    }
     if (p.C % 4 == 0) {
         const int grid = ew_grid(n / 4, num_sms);
         if (bf16) simt::maxpool_vec4_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
@@ -1126,10 +1160,10 @@ static int measure_mma_peak_impl(int device, int precision, float seconds, float
     auto run = [&](int n) -> cudaError_t {
         if (precision == DNNB_BF16) {
             cudaFuncSetAttribute(umma_conv::mma_peak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            umma_conv::mma_peak_kernel<true><<<sms, 64, smem>>>(n);
+            umma_conv::mma_peak_kernel<true><<<sms, 64, smem>>>(n, seconds > 0.f ? 1 : 0);
         } else {
             cudaFuncSetAttribute(umma_conv::mma_peak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            umma_conv::mma_peak_kernel<false><<<sms, 64, smem>>>(n);
+            umma_conv::mma_peak_kernel<false><<<sms, 64, smem>>>(n, seconds > 0.f ? 1 : 0);
         }
         return cudaGetLastError();
     };

@@ -229,6 +229,40 @@ __global__ void __launch_bounds__(256) maxpool_vec4_kernel(const PoolParams p) {
     }
 }
 
+// The stride-1 SAME 2x2 pool of block 5 (proj3/yolov2tiny.py:64; pads bottom/right only,
+// proj3/dnn_openblas.py:127-142 gives front 0 / back 1).  One block per output row, one thread per
+// 4 channels, sliding along x: the vertical max of column x is computed once and used by outputs
+// x-1 and x, so every input element is loaded exactly twice (rows y and y+1) instead of four times.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_2x2s1_kernel(const PoolParams p) {
+    typedef typename Vec4<T>::raw Raw;
+    const int c4 = p.C >> 2;
+    const int b = blockIdx.x / p.OH, oy = blockIdx.x - b * p.OH;
+    const Raw *row0 = static_cast<const Raw *>(p.in) + ((size_t)b * p.IH + oy) * p.IW * c4;
+    const Raw *row1 = row0 + (size_t)p.IW * c4;
+    const bool has1 = oy + 1 < p.IH;
+    Raw *out = static_cast<Raw *>(p.out) + ((size_t)b * p.OH + oy) * p.OW * c4;
+    for (int c = threadIdx.x; c < c4; c += blockDim.x) {
+        float prev[4];
+        for (int x = 0; x < p.IW; ++x) {
+            float v0[4], v1[4], vm[4];
+            Vec4<T>::unpack(__ldg(row0 + (size_t)x * c4 + c), v0);
+            if (has1) Vec4<T>::unpack(__ldg(row1 + (size_t)x * c4 + c), v1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vm[k] = has1 ? (v0[k] >= v1[k] ? v0[k] : v1[k]) : v0[k];
+            if (x > 0) {
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = prev[k] >= vm[k] ? prev[k] : vm[k];
+                out[(size_t)(x - 1) * c4 + c] = Vec4<T>::pack(o);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) prev[k] = vm[k];
+        }
+        out[(size_t)(p.IW - 1) * c4 + c] = Vec4<T>::pack(prev);     // last column: the window's right half is padding
+    }
+}
+
 // ---- op-level element-wise kernels (bit-exact restatements of proj3/dnn_openblas.c) ----------
 __global__ void bias_add_kernel(const float *in, const float *bias, float *out, size_t n, int d) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -151,8 +151,9 @@ int dnnb_host_free(void *p);
  * (precision 1) with a register-free MMA issue loop on every SM: the tensor-pipe roofline
  * denominator for TF32, which MEASURED_PEAKS.json does not hold. */
 int dnnb_measure_mma_peak(int device, int precision, float *tflops);
-/* The same loop run back to back for `seconds` (<= 30): the rate the part settles at under its
- * power cap, the denominator for a kernel timed inside a long step. */
+/* The same loop on pseudo-random operands (the burst probe multiplies zeros, which draws little
+ * power) run back to back for `seconds` (<= 30): the rate the part settles at under its power cap,
+ * the denominator for a kernel timed inside a long step. */
 int dnnb_measure_mma_peak_sustained(int device, int precision, float seconds, float *tflops);
 
 #ifdef __cplusplus

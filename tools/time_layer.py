@@ -13,9 +13,10 @@ from synth import CHANNELS, make_weights  # noqa: E402
 
 layer, batch = int(sys.argv[1]), int(sys.argv[2])
 prec = sys.argv[3] if len(sys.argv) > 3 else "tf32"
+pool = not (len(sys.argv) > 4 and sys.argv[4] == "nopool")
 w = make_weights(0)[layer]
 x = np.random.default_rng(1).random((batch, HW[layer], HW[layer], CHANNELS[layer]), dtype=np.float32)
-net = _lib.Net(x.shape, [spec(layer, w)], precision=prec)
+net = _lib.Net(x.shape, [spec(layer, w, pool)], precision=prec)
 net.forward(x)
 ms = net.time_blocks(3, 10)
 print("layer %d batch %d %s %s: %.4f ms  [%s]" % (layer, batch, prec, net.block_info(0)["kernel"], ms[0],
