@@ -21,9 +21,11 @@
 // The tiles are small, so every per-tile handshake counts: measured on B200 the barrier skeleton
 // alone costs ~200 cycles per tile, which is why a tile is 8 rows and not one pooling row pair.
 //
-// Warp roles (576 threads): 8 producer warps that build each patch together and keep the next
-// tile's global loads in flight in registers while converting the current one; 2 MMA warps and
-// 2 x 4 epilogue warps that alternate tiles.  A CTA owns a contiguous range of tiles and walks
+// Warp roles (608 threads): one loader thread streams the raw 12-byte pixels global -> shared with bulk
+// async copies (one per patch row, kRawDepth tiles ahead); 8 producer warps convert them into the padded
+// patch; 2 MMA warps and 2 x 4 epilogue warps alternate tiles.  The loads must not be issued by the
+// converting threads: their generic->async proxy fence (a MEMBAR) would wait for every load in flight
+// and serialise the prefetch -- measured: one global-load latency per tile.  A CTA owns a contiguous range of tiles and walks
 // (column tile, row tile, image) incrementally.
 //
 // Ring discipline: every patch stage and accumulator stage has the same producer(s) and the same
@@ -40,7 +42,8 @@ namespace conv0 {
 constexpr int kProducerWarps = 8;
 constexpr int kMmaWarps = 2;
 constexpr int kEpilogueGroups = 2;
-constexpr int kThreads = (kProducerWarps + kMmaWarps + 4 * kEpilogueGroups) * 32;
+constexpr int kLoaderWarp = kProducerWarps + kMmaWarps + 4 * kEpilogueGroups;   // one thread of it issues the bulk copies
+constexpr int kThreads = (kLoaderWarp + 1) * 32;
 constexpr int kTileRows = 8;                       // output rows per tile
 constexpr int kPatchRows = kTileRows + 2;
 constexpr int kStages = 4;                         // patch ring
@@ -54,7 +57,10 @@ constexpr int kPatchRowBytes = kPatchPx * 16;
 constexpr int kPatchBytes = kPatchRows * kPatchRowBytes;
 constexpr int kWOperandBytes = 2 * 48 * 16;        // one stacked operand: 2 K halves x 48 rows x 16 B
 constexpr int kWBytes = 2 * kWOperandBytes;        // tap pairs (dj 0,1) and (dj 2, -)
-constexpr int kSmemBytes = kStages * kPatchBytes + kWBytes + 1024 + 256;
+constexpr int kRawDepth = 6;                       // raw-pixel staging ring: tiles whose global loads are in flight
+constexpr int kRawRowBytes = kPatchPx * 12;        // one patch row of raw 12-byte pixels (= kGroups * 48)
+constexpr int kRawBytes = (kPatchRows * kRawRowBytes + 127) / 128 * 128;
+constexpr int kSmemBytes = kStages * kPatchBytes + kRawDepth * kRawBytes + kWBytes + 1024 + 256;
 static_assert(kStages % kMmaWarps == 0 && kAccStages % kMmaWarps == 0 && kAccStages % kEpilogueGroups == 0,
               "one owner warp per ring slot");
 static_assert(kAccCols * kAccStages <= 512, "accumulators must fit TMEM");
@@ -79,8 +85,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint8_t *s_patch = smem;
-    uint8_t *s_w = smem + kStages * kPatchBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + kWBytes);     // full[S], empty[S], tfull[A], tempty[A]
+    uint8_t *s_raw = smem + kStages * kPatchBytes;
+    uint8_t *s_w = s_raw + kRawDepth * kRawBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_w + kWBytes);     // full[S], empty[S], tfull[A], tempty[A], rfull[D], rempty[D]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_w + kWBytes + 512);
     float *s_scale = reinterpret_cast<float *>(s_w + kWBytes + 1024);
     float *s_shift = s_scale + 16;
@@ -89,6 +96,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     const uint32_t bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
     const uint32_t bar_tempty = bar_tfull + 8 * kAccStages;
+    const uint32_t bar_rfull = bar_tempty + 8 * kAccStages;
+    const uint32_t bar_rempty = bar_rfull + 8 * kRawDepth;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_tiles = p.H / kTileRows;
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
         for (int s = 0; s < kAccStages; ++s) { ptx::mbar_init(bar_tfull + 8 * s, 1); ptx::mbar_init(bar_tempty + 8 * s, 128); }
+        for (int s = 0; s < kRawDepth; ++s) { ptx::mbar_init(bar_rfull + 8 * s, 1); ptx::mbar_init(bar_rempty + 8 * s, kProducerWarps); }
         ptx::fence_barrier_init();
     }
     if (warp == kProducerWarps) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), kAccCols * kAccStages);
@@ -145,53 +155,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             g_src[it] = (r * p.W + 4 * gx - 4) * 3;
             g_dst[it] = r * kPatchRowBytes + gx * 64;
         }
-        float4 nxt[kRounds][3];
-        auto issue_loads = [&](const Coord &c) {
-            // pointer to pixel (row 8 jt - 1, column w0) of image n; only dereferenced where in range
-            const int row0 = kTileRows * c.jt - 1, w0 = c.ct * 128;
-            const float *base = p.in + ((size_t)c.n * p.H * p.W + (long long)row0 * p.W + w0) * 3;
-#pragma unroll
-            for (int it = 0; it < kRounds; ++it) {
-                const bool ok = (unsigned)(row0 + g_row[it]) < (unsigned)p.H && (unsigned)(w0 + g_px[it]) < (unsigned)p.W;
-                if (ok) {
-                    const float4 *src = reinterpret_cast<const float4 *>(base + g_src[it]);
-                    nxt[it][0] = __ldg(src); nxt[it][1] = __ldg(src + 1); nxt[it][2] = __ldg(src + 2);
-                } else {
-                    nxt[it][0] = nxt[it][1] = nxt[it][2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-        };
         Coord tc = decode(tile_begin);
-        if (my_tiles > 0) issue_loads(tc);
-        for (int t = 0; t < my_tiles; ++t) {
-            float4 cur[kRounds][3];
-#pragma unroll
-            for (int it = 0; it < kRounds; ++it) { cur[it][0] = nxt[it][0]; cur[it][1] = nxt[it][1]; cur[it][2] = nxt[it][2]; }
-            advance(tc, 1);
-            if (t + 1 < my_tiles) issue_loads(tc);                  // next tile's loads fly while this one is stored
-            const int stage = t % kStages;
-            ptx::mbar_wait(bar_empty + 8 * stage, ((t / kStages) & 1) ^ 1);
+        for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
+            const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
+            const int slot = t % kRawDepth, stage = t % kStages;
+            ptx::mbar_wait(bar_rfull + 8 * slot, (t / kRawDepth) & 1);        // raw pixels have landed
+            ptx::mbar_wait(bar_empty + 8 * stage, ((t / kStages) & 1) ^ 1);    // patch slot is free
             uint8_t *patch = s_patch + stage * kPatchBytes;
+            const uint8_t *raw = s_raw + slot * kRawBytes;
 #pragma unroll
             for (int it = 0; it < kRounds; ++it) {
                 if (g_row[it] < kPatchRows) {
+                    const bool ok = (unsigned)(row0 + g_row[it]) < (unsigned)p.H && (unsigned)(w0 + g_px[it]) < (unsigned)p.W;
+                    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a;      // outside the image: zeros (SAME padding)
+                    if (ok) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(raw + (threadIdx.x + kProducerWarps * 32 * it) * 48);
+                        a = src[0]; b = src[1]; c = src[2];
+                    }
+                    const uint32_t f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
                     uint4 *dst = reinterpret_cast<uint4 *>(patch + g_dst[it]);
-                    const float f[12] = {cur[it][0].x, cur[it][0].y, cur[it][0].z, cur[it][0].w, cur[it][1].x, cur[it][1].y,
-                                         cur[it][1].z, cur[it][1].w, cur[it][2].x, cur[it][2].y, cur[it][2].z, cur[it][2].w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 o;
                         if constexpr (BF16) {
-                            __nv_bfloat162 rg = __floats2bfloat162_rn(f[3 * q], f[3 * q + 1]);
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[3 * q + 2], 0.f);
+                            __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f[3 * q]), __uint_as_float(f[3 * q + 1]));
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(f[3 * q + 2]), 0.f);
                             o.x = *reinterpret_cast<uint32_t *>(&rg);
                             o.y = *reinterpret_cast<uint32_t *>(&b0);
                             o.z = 0u; o.w = 0u;
                         } else {
                             // round to nearest TF32: add half an ulp; the MMA drops the low 13 bits itself
-                            o.x = __float_as_uint(f[3 * q]) + 0x1000u;
-                            o.y = __float_as_uint(f[3 * q + 1]) + 0x1000u;
-                            o.z = __float_as_uint(f[3 * q + 2]) + 0x1000u;
+                            o.x = ok ? f[3 * q] + 0x1000u : 0u;
+                            o.y = ok ? f[3 * q + 1] + 0x1000u : 0u;
+                            o.z = ok ? f[3 * q + 2] + 0x1000u : 0u;
                             o.w = 0u;
                         }
                         dst[q] = o;
@@ -200,7 +196,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
+            if (lane == 0) {
+                ptx::mbar_arrive(bar_rempty + 8 * slot);      // raw slot may be refilled
+                ptx::mbar_arrive(bar_full + 8 * stage);       // patch ready for the MMAs
+            }
+        }
+    } else if (warp == kLoaderWarp) {
+        // ------------------------------------------------------------ raw-pixel loader (one thread)
+        if (ptx::elect_one()) {
+            const uint32_t raw_base = ptx::smem_u32(s_raw);
+            Coord tc = decode(tile_begin);
+            for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
+                const int slot = t % kRawDepth;
+                ptx::mbar_wait(bar_rempty + 8 * slot, ((t / kRawDepth) & 1) ^ 1);
+                const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
+                const int px_lo = w0 - 4 > 0 ? w0 - 4 : 0;
+                const int px_hi = w0 + kPatchPx - 4 < p.W ? w0 + kPatchPx - 4 : p.W;
+                const int r_lo = row0 < 0 ? -row0 : 0;
+                const int r_hi = row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0;
+                const uint32_t bytes = (uint32_t)(px_hi - px_lo) * 12u;       // multiple of 48: pixels come in fours
+                ptx::mbar_expect_tx(bar_rfull + 8 * slot, bytes * (uint32_t)(r_hi - r_lo));
+                const float *src = p.in + (((size_t)tc.n * p.H + (row0 + r_lo)) * p.W + px_lo) * 3;
+                uint32_t dst = raw_base + slot * kRawBytes + r_lo * kRawRowBytes + (px_lo - (w0 - 4)) * 12;
+                for (int r = r_lo; r < r_hi; ++r, src += (size_t)p.W * 3, dst += kRawRowBytes)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_rfull + 8 * slot) : "memory");
+            }
         }
     } else if (warp < kProducerWarps + kMmaWarps) {
         // ------------------------------------------------------------ MMA issuers
