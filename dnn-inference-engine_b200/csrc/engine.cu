@@ -288,7 +288,15 @@ struct dnnb_net {
     std::vector<Block> blocks;
     bool finalized = false;
     cudaStream_t stream = nullptr;
-    float *d_in = nullptr;        // fp32 staging of the host input
+    float *d_in = nullptr;        // fp32 staging of the host input (= d_in2[0])
+    // host path pipelining: H2D of forward i+1 and D2H of forward i-1 overlap the kernels of forward i
+    float *d_in2[2] = {nullptr, nullptr};
+    float *d_outf[2] = {nullptr, nullptr};   // final fp32 outputs, alternating (d_outf[0] is the last block's own buffer)
+    const float *last_final = nullptr;       // where the most recent forward left its result
+    const void *last_in = nullptr;           // fp32 device input of the most recent forward
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
+    int flip = 0;
     void *d_in_cast = nullptr;    // input in the first tcgen05 block's storage type
     float *d_out_f32 = nullptr;   // fp32 copy of the last output when it is stored as bf16
     void *d_flush = nullptr;      // L2 flush scratch for dnnb_net_time_blocks
@@ -934,7 +942,17 @@ int dnnb_net_finalize(dnnb_net *net) {
         h = b.oh; w = b.ow;
     }
     const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
-    CK(cudaMalloc(&net->d_in, n_in * 4));
+    CK(cudaMalloc(&net->d_in2[0], n_in * 4));
+    CK(cudaMalloc(&net->d_in2[1], n_in * 4));
+    net->d_in = net->d_in2[0];
+    CK(cudaStreamCreateWithFlags(&net->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&net->copy_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaEventCreateWithFlags(&net->in_ready[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&net->in_free[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&net->out_ready[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&net->out_free[k], cudaEventDisableTiming));
+    }
     Block &first = net->blocks.front();
     if (first.family != DNNB_KERNEL_SIMT && first.family != DNNB_KERNEL_UMMA_CONV0) {
         CK(cudaMalloc(&net->d_in_cast, n_in * (first.in_bf16 ? 2 : 4)));
@@ -972,6 +990,8 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
     if (!dev_in) return fail("null device input");
     DeviceGuard g(net->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
+    net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
+    net->last_in = dev_in;
     return forward_impl(net, dev_in, dev_out, st);
 }
 
@@ -980,10 +1000,29 @@ int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out)
     if (!host_in || !host_out) return fail("null host buffer");
     DeviceGuard g(net->device);
     const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
-    CK(cudaMemcpyAsync(net->d_in, host_in, n_in * 4, cudaMemcpyHostToDevice, net->stream));
-    if (forward_impl(net, net->d_in, nullptr, net->stream)) return 1;
-    const Block &l = net->blocks.back();
-    CK(cudaMemcpyAsync(host_out, l.d_out, l.out_elems * 4, cudaMemcpyDeviceToHost, net->stream));
+    Block &l = net->blocks.back();
+    if (!net->d_outf[0]) {
+        net->d_outf[0] = static_cast<float *>(l.d_out);
+        CK(cudaMalloc(&net->d_outf[1], l.out_elems * 4));
+    }
+    const int k = net->flip;
+    net->flip ^= 1;
+    // H2D on its own stream, as soon as the forward that last read this input buffer is done
+    CK(cudaStreamWaitEvent(net->copy_in, net->in_free[k], 0));
+    CK(cudaMemcpyAsync(net->d_in2[k], host_in, n_in * 4, cudaMemcpyHostToDevice, net->copy_in));
+    CK(cudaEventRecord(net->in_ready[k], net->copy_in));
+    // kernels: need the input, and the output buffer's previous D2H must have drained
+    CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
+    CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
+    if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
+    CK(cudaEventRecord(net->in_free[k], net->stream));
+    CK(cudaEventRecord(net->out_ready[k], net->stream));
+    // D2H on a third stream
+    CK(cudaStreamWaitEvent(net->copy_out, net->out_ready[k], 0));
+    CK(cudaMemcpyAsync(host_out, net->d_outf[k], l.out_elems * 4, cudaMemcpyDeviceToHost, net->copy_out));
+    CK(cudaEventRecord(net->out_free[k], net->copy_out));
+    net->last_final = net->d_outf[k];
+    net->last_in = net->d_in2[k];
     return 0;
 }
 
@@ -991,6 +1030,8 @@ int dnnb_net_sync(dnnb_net *net) {
     if (check_net(net, false)) return 1;
     DeviceGuard g(net->device);
     CK(cudaStreamSynchronize(net->stream));
+    if (net->copy_in) CK(cudaStreamSynchronize(net->copy_in));
+    if (net->copy_out) CK(cudaStreamSynchronize(net->copy_out));
     return 0;
 }
 
@@ -1006,7 +1047,9 @@ int dnnb_net_block_output(dnnb_net *net, int block, float *host_out) {
     Block &b = net->blocks[block];
     CK(cudaStreamSynchronize(net->stream));
     if (!b.out_bf16) {
-        CK(cudaMemcpy(host_out, b.d_out, b.out_elems * 4, cudaMemcpyDeviceToHost));
+        const void *src = b.d_out;
+        if (block + 1 == (int)net->blocks.size() && net->last_final) src = net->last_final;
+        CK(cudaMemcpy(host_out, src, b.out_elems * 4, cudaMemcpyDeviceToHost));
     } else {
         DevBuf tmp;
         if (tmp.alloc(b.out_elems * 4)) return 1;
@@ -1027,7 +1070,8 @@ int dnnb_net_debug_prepool(dnnb_net *net, int block, float *host_out) {
     const size_t n = (size_t)net->B * b.ch * b.cw * b.oc;
     DevBuf tmp;
     if (tmp.alloc(n * 4)) return 1;
-    const void *in = block == 0 ? (net->d_in_cast ? net->d_in_cast : (const void *)net->d_in) : net->blocks[block - 1].d_out;
+    const void *in = block == 0 ? (net->d_in_cast ? net->d_in_cast : (net->last_in ? net->last_in : (const void *)net->d_in))
+                                : net->blocks[block - 1].d_out;
     CK(cudaStreamSynchronize(net->stream));
     if (run_block(net, b, in, nullptr, net->stream, tmp.f())) return 1;
     CK(cudaStreamSynchronize(net->stream));
@@ -1127,7 +1171,17 @@ int dnnb_net_destroy(dnnb_net *net) {
         if (b.d_shift) cudaFree(b.d_shift);
     }
     for (auto &pr : net->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    if (net->d_in) cudaFree(net->d_in);
+    if (net->d_in2[0]) cudaFree(net->d_in2[0]);
+    if (net->d_in2[1]) cudaFree(net->d_in2[1]);
+    if (net->d_outf[1]) cudaFree(net->d_outf[1]);
+    for (int k = 0; k < 2; ++k) {
+        if (net->in_ready[k]) cudaEventDestroy(net->in_ready[k]);
+        if (net->in_free[k]) cudaEventDestroy(net->in_free[k]);
+        if (net->out_ready[k]) cudaEventDestroy(net->out_ready[k]);
+        if (net->out_free[k]) cudaEventDestroy(net->out_free[k]);
+    }
+    if (net->copy_in) cudaStreamDestroy(net->copy_in);
+    if (net->copy_out) cudaStreamDestroy(net->copy_out);
     if (net->d_in_cast) cudaFree(net->d_in_cast);
     if (net->d_out_f32) cudaFree(net->d_out_f32);
     if (net->d_flush) cudaFree(net->d_flush);
