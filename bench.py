@@ -69,51 +69,55 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every
+    few ms from a thread (nvidia-smi's loop is too coarse for a 60 ms region); nvidia-smi as fallback."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period, self.samples, self.stop_flag, self.thread, self.err = index, period_s, [], False, None, None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, rs))
+                time.sleep(self.period)
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return self._smi_once()
+        sm = [s[0] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[2]
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": self.samples[0][1], "samples": len(sm),
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit), "source": "nvml"}
+
+    def _smi_once(self):
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(v) for v in out.strip().split(",")]
+            return {"sm_mhz": a, "sm_max_mhz": b, "samples": 1, "reasons": [], "source": "nvidia-smi after the region (nvml failed: %s)" % self.err}
+        except Exception:   # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable: %s" % self.err]}
 
 
 def openblas_threads():
@@ -308,7 +312,31 @@ def run_b200(args):
                "steps": k_e2e, "matches_device_path": same,
                "note": "per micro-batch: cudaMemcpyAsync H2D -> 9 fused blocks -> cudaMemcpyAsync D2H, on three streams so the "
                        "copies of neighbouring micro-batches overlap the kernels (double-buffered input and output)"}
-        hin.free(); hout.free()
+        hin.free()
+        # the same through the uint8-frame entry point: 3 bytes per pixel over PCIe, /255 on the device
+        hu8 = _lib.PinnedArray((n_mb, mb, 416, 416, 3), dtype=np.uint8)
+        u8 = hu8.array
+        u8[...] = np.random.default_rng(5 + rank).integers(0, 256, size=(mb, 416, 416, 3), dtype=np.uint8)[None]
+
+        def e2e_u8_step():
+            for j in range(n_mb):
+                net.forward_u8_async(u8[j], hout.array[j], True)
+            net.sync()
+
+        e2e_u8_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_u8_step()
+        fence()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["uint8_frames"] = {"value": args.global_batch * k_e2e / float(dt.item()), "unit": UNIT,
+                               "h2d_bytes_per_step": int(args.global_batch * 416 * 416 * 3),
+                               "note": "dnnb_net_forward_u8_async: uint8 BGR frames in, float32(u8/255.) + BGR->RGB "
+                                       "(proj3/__init__.py:8-12 minus the resize) as one extra kernel on the device"}
+        hu8.free(); hout.free()
 
     # ---- per-layer roofline (micro-batch, L2 flushed between repetitions)
     peaks = measured_peaks()
@@ -350,7 +378,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
-            "e2e": e2e, "gpu_launches": net.launches_per_forward() * n_mb * args.steps,
+            "e2e": e2e, "gpu_launches": net.launches_per_forward() * n_mb * args.steps,   # timed region of `value`
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "layers": layers,
             "sum_layer_roofline_frac": (sum(max(algorithmic_bytes(i, mb, act_bytes) / (peaks["hbm_gbs"] * 1e9),
                                                  GFLOP_PER_IMAGE[i] * 1e9 * mb / (tensor_peak * 1e12)) for i in range(9))

@@ -51,6 +51,8 @@ _sig("dnnb_net_out_shape", c_void_p, IP, IP, IP, IP)
 _sig("dnnb_net_forward", c_void_p, c_void_p, c_void_p)
 _sig("dnnb_net_forward_async", c_void_p, c_void_p, c_void_p)
 _sig("dnnb_net_forward_device", c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_forward_u8_async", c_void_p, c_void_p, c_int, c_void_p)
+_sig("dnnb_net_forward_u8_device", c_void_p, c_void_p, c_int, c_void_p, c_void_p)
 _sig("dnnb_net_sync", c_void_p)
 _sig("dnnb_net_block_output", c_void_p, c_int, FP)
 _sig("dnnb_net_block_info", c_void_p, c_int, IP)
@@ -68,7 +70,7 @@ _sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
-           "dnnb_net_forward_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
+           "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained"]
 
@@ -94,15 +96,15 @@ def device_count():
 
 
 class PinnedArray:
-    """A float32 numpy array over page-locked host memory (async H2D/D2H)."""
+    """A numpy array (float32 by default) over page-locked host memory (async H2D/D2H)."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, dtype=np.float32):
         self.shape = tuple(int(s) for s in shape)
-        n = int(np.prod(self.shape))
+        nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
         self._ptr = c_void_p()
-        check(lib.dnnb_host_alloc(n * 4, ctypes.byref(self._ptr)))
-        buf = (c_float * n).from_address(self._ptr.value)
-        self.array = np.frombuffer(buf, dtype=np.float32).reshape(self.shape)
+        check(lib.dnnb_host_alloc(nbytes, ctypes.byref(self._ptr)))
+        buf = (ctypes.c_ubyte * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
 
     def free(self):
         if self._ptr is not None and self._ptr.value:
@@ -173,6 +175,20 @@ class Net:
     def forward_async(self, x, out):
         """x, out: C-contiguous float32 arrays (ideally PinnedArray.array) kept alive until sync()."""
         check(lib.dnnb_net_forward_async(self._h, x.ctypes.data, out.ctypes.data))
+
+    def forward_u8(self, frames, bgr=True, out=None):
+        """frames: uint8 [B,H,W,3] (BGR as cv2 delivers them when bgr=True).  x = float32(u8/255.) with the
+        channel reversal of proj3/__init__.py:8-12 happens on the device."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert tuple(frames.shape) == self.in_shape, (frames.shape, self.in_shape)
+        if out is None:
+            out = np.empty(self.out_shape, dtype=np.float32)
+        self.forward_u8_async(frames, out, bgr)
+        self.sync()
+        return out
+
+    def forward_u8_async(self, frames, out, bgr=True):
+        check(lib.dnnb_net_forward_u8_async(self._h, frames.ctypes.data, 1 if bgr else 0, out.ctypes.data))
 
     def forward_device(self, in_ptr, out_ptr=None, stream=None):
         check(lib.dnnb_net_forward_device(self._h, in_ptr, out_ptr, stream))

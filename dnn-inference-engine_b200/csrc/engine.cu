@@ -294,6 +294,9 @@ struct dnnb_net {
     float *d_outf[2] = {nullptr, nullptr};   // final fp32 outputs, alternating (d_outf[0] is the last block's own buffer)
     const float *last_final = nullptr;       // where the most recent forward left its result
     const void *last_in = nullptr;           // fp32 device input of the most recent forward
+    // uint8 frames (proj3/__init__.py:8-12 without the resize): staging + the /255 table
+    uint8_t *d_u8[2] = {nullptr, nullptr};
+    float *d_lut = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
     int flip = 0;
@@ -1026,6 +1029,71 @@ int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out)
     return 0;
 }
 
+namespace {
+int ensure_u8(dnnb_net *net) {
+    if (net->C != 3) return fail("uint8 frames need a 3-channel network input");
+    const size_t n = (size_t)net->B * net->H * net->W * 3;
+    if (n % 12 != 0) return fail("uint8 frames: B*H*W must be a multiple of 4");
+    if (!net->d_lut) {
+        float lut[256];
+        for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);   // numpy: uint8 / 255. -> float64 -> float32
+        CK(cudaMalloc(&net->d_lut, sizeof(lut)));
+        CK(cudaMemcpy(net->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&net->d_u8[0], n));
+        CK(cudaMalloc(&net->d_u8[1], n));
+    }
+    return 0;
+}
+cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f32, int swap_rb, cudaStream_t st) {
+    const size_t groups = (size_t)net->B * net->H * net->W / 4;
+    simt::preprocess_u8_kernel<<<ew_grid(groups, net->num_sms), 256, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(dev_u8), reinterpret_cast<float4 *>(dev_f32), groups, net->d_lut, swap_rb);
+    return cudaGetLastError();
+}
+}  // namespace
+
+int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void *dev_out, void *stream) {
+    if (check_net(net, true)) return 1;
+    if (!dev_u8) return fail("null device input");
+    DeviceGuard g(net->device);
+    if (ensure_u8(net)) return 1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
+    CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_u8), net->d_in2[0], bgr ? 1 : 0, st));
+    net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
+    net->last_in = net->d_in2[0];
+    return forward_impl(net, net->d_in2[0], dev_out, st);
+}
+
+int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, float *host_out) {
+    if (check_net(net, true)) return 1;
+    if (!host_u8 || !host_out) return fail("null host buffer");
+    DeviceGuard g(net->device);
+    if (ensure_u8(net)) return 1;
+    const size_t n_in = (size_t)net->B * net->H * net->W * 3;
+    Block &l = net->blocks.back();
+    if (!net->d_outf[0]) {
+        net->d_outf[0] = static_cast<float *>(l.d_out);
+        CK(cudaMalloc(&net->d_outf[1], l.out_elems * 4));
+    }
+    const int k = net->flip;
+    net->flip ^= 1;
+    CK(cudaStreamWaitEvent(net->copy_in, net->in_free[k], 0));
+    CK(cudaMemcpyAsync(net->d_u8[k], host_u8, n_in, cudaMemcpyHostToDevice, net->copy_in));
+    CK(cudaEventRecord(net->in_ready[k], net->copy_in));
+    CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
+    CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
+    CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], bgr ? 1 : 0, net->stream));
+    if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
+    CK(cudaEventRecord(net->in_free[k], net->stream));
+    CK(cudaEventRecord(net->out_ready[k], net->stream));
+    CK(cudaStreamWaitEvent(net->copy_out, net->out_ready[k], 0));
+    CK(cudaMemcpyAsync(host_out, net->d_outf[k], l.out_elems * 4, cudaMemcpyDeviceToHost, net->copy_out));
+    CK(cudaEventRecord(net->out_free[k], net->copy_out));
+    net->last_final = net->d_outf[k];
+    net->last_in = net->d_in2[k];
+    return 0;
+}
+
 int dnnb_net_sync(dnnb_net *net) {
     if (check_net(net, false)) return 1;
     DeviceGuard g(net->device);
@@ -1174,6 +1242,9 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->d_in2[0]) cudaFree(net->d_in2[0]);
     if (net->d_in2[1]) cudaFree(net->d_in2[1]);
     if (net->d_outf[1]) cudaFree(net->d_outf[1]);
+    if (net->d_u8[0]) cudaFree(net->d_u8[0]);
+    if (net->d_u8[1]) cudaFree(net->d_u8[1]);
+    if (net->d_lut) cudaFree(net->d_lut);
     for (int k = 0; k < 2; ++k) {
         if (net->in_ready[k]) cudaEventDestroy(net->in_ready[k]);
         if (net->in_free[k]) cudaEventDestroy(net->in_free[k]);

@@ -292,6 +292,34 @@ __global__ void cast_input_kernel(const float *in, TOut *out, size_t n, int roun
         out[i] = from_f32<TOut>(v);
     }
 }
+// Device half of proj3/__init__.py:8-12 (resize_input) for frames that already are 416x416:
+//   imsz = frame / 255.   (uint8 -> float64)      imsz = imsz[:, :, ::-1]  (BGR -> RGB)      float32(imsz)
+// lut[v] = (float)((double)v / 255.0) is computed on the host, so the result is bit-identical to numpy's.
+// One thread = 4 pixels = 12 bytes in, 48 bytes out.
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint32_t *in, float4 *out, size_t groups,
+                                                            const float *lut_g, int swap_rb) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = lut_g[threadIdx.x];
+    __syncthreads();
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t w0 = __ldg(in + 3 * g), w1 = __ldg(in + 3 * g + 1), w2 = __ldg(in + 3 * g + 2);
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = lut[(w0 >> (8 * k)) & 0xff];
+            v[4 + k] = lut[(w1 >> (8 * k)) & 0xff];
+            v[8 + k] = lut[(w2 >> (8 * k)) & 0xff];
+        }
+        if (swap_rb) {
+#pragma unroll
+            for (int px = 0; px < 4; ++px) { const float t = v[3 * px]; v[3 * px] = v[3 * px + 2]; v[3 * px + 2] = t; }
+        }
+        out[3 * g] = make_float4(v[0], v[1], v[2], v[3]);
+        out[3 * g + 1] = make_float4(v[4], v[5], v[6], v[7]);
+        out[3 * g + 2] = make_float4(v[8], v[9], v[10], v[11]);
+    }
+}
+
 template <typename TIn>
 __global__ void cast_output_kernel(const TIn *in, float *out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

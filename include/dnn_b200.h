@@ -108,6 +108,14 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
  * dnnb_net_sync returns.  Lets one host thread keep several devices busy. */
 int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out);
 
+/* uint8 frames: the device half of proj3/__init__.py:8-12 (resize_input) for frames that already are
+ * in_h x in_w -- x = float32(u8 / 255.), and with bgr != 0 the channel reversal imsz[:, :, ::-1] --
+ * runs as one extra kernel in front of block 0, so only 3 bytes per pixel cross PCIe instead of 12.
+ * Bit-identical to feeding dnnb_net_forward the numpy-preprocessed float32 array.  3-channel inputs only.
+ * The async form pipelines like dnnb_net_forward_async (page-locked buffers, dnnb_net_sync). */
+int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, float *host_out);
+int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void *dev_out, void *stream);
+
 /* Waits for everything queued on the network's own stream. */
 int dnnb_net_sync(dnnb_net *net);
 

@@ -274,6 +274,25 @@ def test_full_size_batch256_properties(oracle_libs):
     eng.close(); eng1.close()
 
 
+def test_uint8_frames_match_numpy_preprocessing():
+    """proj3/__init__.py:8-12 minus the resize.  The device-side /255 + BGR->RGB must be
+    bit-identical to numpy's, so the network output equals the float32 path's exactly."""
+    rng = np.random.default_rng(77)
+    frames = rng.integers(0, 256, size=(3, 416, 416, 3), dtype=np.uint8)
+    x = np.asarray((frames / 255.)[:, :, :, ::-1], dtype=np.float32)      # resize_input's arithmetic
+    g = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g, [3, 416, 416, 3], make_weights(0))
+    eng = dnn_b200.DnnInferenceEngine(g, False, precision="tf32")
+    ref = eng.run(x).copy()
+    got = eng._net.forward_u8(frames, bgr=True)
+    np.testing.assert_array_equal(got, ref)
+    got_rgb = eng._net.forward_u8(np.ascontiguousarray(frames[..., ::-1]), bgr=False)
+    np.testing.assert_array_equal(got_rgb, ref)
+    got2 = eng._net.forward_u8(frames, bgr=True)      # second call: the other half of the double buffers
+    np.testing.assert_array_equal(got2, ref)
+    eng.close()
+
+
 def test_debug_mode_runs_node_by_node_and_dumps_layers(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     gold = np.load(os.path.join(GOLDEN, "mini_net.npz"))
