@@ -15,7 +15,8 @@
 //   * im2col mode: 128 consecutive output pixels (running over rows and images) through a
 //                  cuTensorMapEncodeIm2col descriptor; used for the 13x13 layers, whose M
 //                  would otherwise not tile without waste.
-// Weights are prepacked once as [tap][OCp][ICp] (K-major), so the B tile is one 3-D TMA box.
+// Weights are prepacked once as [tap][channel chunk][OCp][BKC] (K-major), so the B tile of a
+// K block is one contiguous TMA box.
 //
 // CTA = 192 threads, persistent over tiles (static round-robin):
 //   warp 0   : TMA producer (one elected lane)          full/empty mbarrier ring, STAGES deep
@@ -49,6 +50,13 @@ struct Params {
     int leaky;
     int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
     float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
+    // split-K (small batches: too few output tiles to fill the SMs, weights dominate the traffic):
+    // `splits` CTAs share one output tile, each reduces a slice of K into `workspace` with vector
+    // atomics; the CTA that arrives last at `counters[tile]` runs the epilogue from the workspace
+    // and leaves workspace and counter zeroed for the next launch.
+    int splits;           // 1 = off
+    float *workspace;     // [num_m_tiles * MT * 128][num_n_tiles * BN] fp32, zero between launches
+    int *counters;        // [num_m_tiles * num_n_tiles], zero between launches
 };
 
 // MT = M tiles (of 128 rows) per CTA tile that share every B tile: MT = 2 turns the CTA tile
@@ -95,6 +103,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t *tail = smem + STAGES * C::STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);           // full[S], empty[S], tfull[2], tempty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
+    volatile int *s_flag = reinterpret_cast<volatile int *>(tail + 520);   // split-K: "this CTA finishes the tile"
     float *s_scale = reinterpret_cast<float *>(tail + 1024);
     float *s_shift = s_scale + 1024;
     float *s_out = s_shift + 1024;       // STAGE_OUT only: [4 warps][32 rows][OC]
@@ -107,9 +116,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = tiles_mn * p.splits;       // work items: (output tile, K slice)
     const int taps = p.KH * p.KW;
     const int num_kstages = taps * p.c_chunks / KBS;
+    // K slice of work item `tile`: stages [ks_lo, ks_hi)
+    auto k_range = [&](int tile, int &ks_lo, int &ks_hi) {
+        const int split = tile / tiles_mn;
+        ks_lo = (int)((long)num_kstages * split / p.splits);
+        ks_hi = (int)((long)num_kstages * (split + 1) / p.splits);
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -141,7 +157,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = tile / p.num_n_tiles;
+                const int m_tile = (tile % tiles_mn) / p.num_n_tiles;
+                int ks_lo, ks_hi;
+                k_range(tile, ks_lo, ks_hi);
                 int w0[MT], h0[MT], n0[MT];
                 if constexpr (IM2COL) {
 #pragma unroll
@@ -160,7 +178,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         n0[i] = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + i) * p.nb;
                     }
                 }
-                for (int ks = 0; ks < num_kstages; ++ks) {
+                for (int ks = ks_lo; ks < ks_hi; ++ks) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
                     ptx::mbar_expect_tx(full, C::STAGE_BYTES);
@@ -181,7 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             else
                                 ptx::tma_load_4d(dst, &map_a, full, cc * BKC, w0[i] + dj - p.PL, h0[i] + di - p.PT, n0[i]);
                         }
-                        ptx::tma_load_3d(sb + j * C::B_TILE, &map_b, full, cc * BKC, n_tile * BN, tap);
+                        ptx::tma_load_4d(sb + j * C::B_TILE, &map_b, full, 0, n_tile * BN, cc, tap);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -201,7 +219,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
-                for (int ks = 0; ks < num_kstages; ++ks) {
+                int ks_lo, ks_hi;
+                k_range(tile, ks_lo, ks_hi);
+                for (int ks = ks_lo; ks < ks_hi; ++ks) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase);
                     ptx::tc_fence_after();
                     const uint32_t a_lo = ptx::umma_desc_lo(smem_base + stage * C::STAGE_BYTES);
@@ -215,7 +235,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 ptx::umma<BF16>(d_tmem + i * BN,
                                                 ptx::umma_desc_join(a_lo + (((j * MT + i) * C::A_TILE + 32 * k) >> 4), HI),
                                                 ptx::umma_desc_join(b_lo + ((j * C::B_TILE + 32 * k) >> 4), HI), idesc,
-                                                (ks | j | k) != 0 ? 1u : 0u);
+                                                ((ks - ks_lo) | j | k) != 0 ? 1u : 0u);
                         }
                     }
                     ptx::umma_commit(bar_empty + 8 * stage);   // smem slot free once these MMAs retire
@@ -233,9 +253,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int acc = local % ACC;
             const uint32_t acc_phase = (local / ACC) & 1;
             const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = tile / p.num_n_tiles;
+            const int m_tile = (tile % tiles_mn) / p.num_n_tiles;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
             ptx::tc_fence_after();
+
+            const bool split_k = p.splits > 1;
+            const int ldw = p.num_n_tiles * BN;
+            if (split_k) {
+                // phase 1: add this K slice's partial sums to the workspace, free the accumulator
+#pragma unroll 1
+                for (int mi = 0; mi < MT; ++mi) {
+                    float *wrow = p.workspace + ((size_t)(m_tile * MT + mi) * kBM + row) * ldw + n_tile * BN;
+#pragma unroll 1
+                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                        uint32_t raw[32];
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + chunk * 32 + j),
+                                         "f"(__uint_as_float(raw[j])), "f"(__uint_as_float(raw[j + 1])),
+                                         "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                                         : "memory");
+                    }
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar_tempty + 8 * acc);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (row == 0) {
+                    const int prev = atomicAdd(p.counters + (tile % tiles_mn), 1);
+                    *s_flag = prev == p.splits - 1 ? 1 : 0;
+                    if (prev == p.splits - 1) p.counters[tile % tiles_mn] = 0;     // leave it ready for the next launch
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *s_flag != 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");    // s_flag may be rewritten by the next work item
+                if (!last) continue;
+                __threadfence();
+            }
 
 #pragma unroll 1
             for (int mi = 0; mi < MT; ++mi) {
@@ -263,8 +319,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll 1
             for (int chunk = 0; chunk < BN / 32; ++chunk) {
                 uint32_t raw[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
-                ptx::tmem_ld_wait();
+                if (split_k) {
+                    // phase 2 (last CTA of the tile): the sums now live in the workspace; read and clear it
+                    float4 *wsrc = reinterpret_cast<float4 *>(p.workspace + ((size_t)(m_tile * MT + mi) * kBM + row) * ldw +
+                                                              n_tile * BN + chunk * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t4 = __ldcg(wsrc + j);
+                        raw[4 * j] = __float_as_uint(t4.x); raw[4 * j + 1] = __float_as_uint(t4.y);
+                        raw[4 * j + 2] = __float_as_uint(t4.z); raw[4 * j + 3] = __float_as_uint(t4.w);
+                        __stcg(wsrc + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                } else {
+                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
+                    ptx::tmem_ld_wait();
+                }
                 const int col0 = n_tile * BN + chunk * 32;
                 float v[32];
 #pragma unroll
@@ -400,8 +469,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
             }
             }   // mi
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_tempty + 8 * acc);
+            if (!split_k) {
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar_tempty + 8 * acc);
+            }
         }
     }
 

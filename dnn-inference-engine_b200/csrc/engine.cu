@@ -275,6 +275,8 @@ struct Block {
     float *d_kernel = nullptr;                  // HWIO fp32 (SIMT)
     void *d_wpack = nullptr;                    // [tap][OCp][IC] tf32-rounded fp32 or bf16
     float *d_scale = nullptr, *d_shift = nullptr;
+    float *d_workspace = nullptr;               // split-K partial sums (zero between launches)
+    int *d_counters = nullptr;                  // split-K arrival counters (zero between launches)
     void *d_conv_out = nullptr;                 // conv(+fused pool) output
     void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
     size_t conv_out_elems = 0, out_elems = 0;
@@ -367,16 +369,28 @@ int encode_map_b(Block &b) {
         if (r != CUDA_SUCCESS) return fail("tensor-map encode (row-pair weights) failed: CUresult %d", (int)r);
         return 0;
     }
+    // [tap][channel chunk][OCp][BKC]: the B tile of a K block (BN rows x one swizzle span) is one
+    // contiguous BN*SWZ-byte run, so cold weights stream from HBM instead of being gathered line by line
     const int ocp = b.up.num_n_tiles * b.bn;
-    cuuint64_t dims[3] = {(cuuint64_t)b.ic, (cuuint64_t)ocp, (cuuint64_t)(b.kh * b.kw)};
-    cuuint64_t strides[2] = {(cuuint64_t)b.ic * es, (cuuint64_t)ocp * b.ic * es};
-    cuuint32_t box[3] = {(cuuint32_t)(b.swz / es), (cuuint32_t)b.bn, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode_tiled(&b.map_b, dt, 3, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const int bkc = b.swz / es;
+    cuuint64_t dims[4] = {(cuuint64_t)bkc, (cuuint64_t)ocp, (cuuint64_t)(b.ic / bkc), (cuuint64_t)(b.kh * b.kw)};
+    cuuint64_t strides[3] = {(cuuint64_t)b.swz, (cuuint64_t)ocp * b.swz, (cuuint64_t)(b.ic / bkc) * ocp * b.swz};
+    cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)b.bn, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(&b.map_b, dt, 4, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("tensor-map encode (weights) failed: CUresult %d", (int)r);
     return 0;
+}
+
+// DNNB_LATENCY_MODE=1 (read when a network is finalized) trades two properties for small-batch
+// latency: split-K sums partial tiles with floating-point atomics, so results are no longer
+// bit-reproducible run to run nor identical across batch sizes (they stay within fp32 reordering
+// noise, ~1e-6 relative); default off.
+bool latency_mode() {
+    const char *v = getenv("DNNB_LATENCY_MODE");
+    return v && v[0] == '1';
 }
 
 // scale/shift + LeakyReLU + rounding is monotone non-decreasing when scale > 0: pooling may then
@@ -462,6 +476,9 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 while (tw * th < 128 && b.ih % (th * 2) == 0) th *= 2;
                 nb = 128 / (tw * th);
                 fuse = tw >= 2 && th >= 2;
+                // a spatial tile spans nb images; with far fewer images in the batch it is mostly padding:
+                // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
+                if (fuse && net->B * 2 <= nb && latency_mode()) fuse = false;
             }
             UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
             const UmmaEntry *e = find_umma(key);
@@ -513,7 +530,16 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 }
                 p.leaky = b.leaky;
                 p.round_tf32 = b.round_tf32;
-                const int tiles = p.num_m_tiles * p.num_n_tiles;
+                // split-K when the output tiles alone cannot occupy the SMs (small batches)
+                const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+                const int kstages = total_kb / kbs;
+                p.splits = 1;
+                if (tiles_mn * 2 <= net->num_sms && kstages >= 8 && latency_mode()) {
+                    int sp = net->num_sms / tiles_mn;
+                    if (sp > kstages / 4) sp = kstages / 4;
+                    if (sp >= 2) p.splits = sp;
+                }
+                const int tiles = tiles_mn * p.splits;
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;
             }
         }
@@ -609,6 +635,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         }
         umma_conv::Params p = b.up;
         p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
+        p.workspace = b.d_workspace; p.counters = b.d_counters;
         CK(b.umma->launch(b.map_a, b.map_b, p, b.grid, st));
     }
     if (b.pool_separate) {
@@ -918,15 +945,19 @@ int dnnb_net_finalize(dnnb_net *net) {
             CK(cudaMemcpy(b.d_kernel, b.kernel.data(), sizeof(float) * b.kernel.size(), cudaMemcpyHostToDevice));
         } else {
             if (b.family != DNNB_KERNEL_UMMA_TILED && b.family != DNNB_KERNEL_UMMA_IM2COL) return fail("internal: unknown kernel family");
-            // prepack HWIO -> [tap][OCp][IC], K-major, rounded once to the MMA operand type
+            // prepack HWIO -> [tap][channel chunk][OCp][BKC], K-major, rounded once to the MMA operand type
             const int taps = b.kh * b.kw;
             const size_t n = (size_t)taps * ocp * b.ic;
+            const int bkc = b.swz / (b.in_bf16 ? 2 : 4), chunks = b.ic / bkc;
+            auto widx = [&](int t, int c, int d) {
+                return (((size_t)t * chunks + c / bkc) * ocp + d) * bkc + c % bkc;
+            };
             if (b.in_bf16) {
                 std::vector<uint16_t> pk(n, 0);
                 for (int t = 0; t < taps; ++t)
                     for (int c = 0; c < b.ic; ++c)
                         for (int d = 0; d < b.oc; ++d)
-                            pk[((size_t)t * ocp + d) * b.ic + c] = host_bf16(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
+                            pk[widx(t, c, d)] = host_bf16(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
                 CK(cudaMalloc(&b.d_wpack, n * 2));
                 CK(cudaMemcpy(b.d_wpack, pk.data(), n * 2, cudaMemcpyHostToDevice));
             } else {
@@ -934,11 +965,19 @@ int dnnb_net_finalize(dnnb_net *net) {
                 for (int t = 0; t < taps; ++t)
                     for (int c = 0; c < b.ic; ++c)
                         for (int d = 0; d < b.oc; ++d)
-                            pk[((size_t)t * ocp + d) * b.ic + c] = host_round_tf32(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
+                            pk[widx(t, c, d)] = host_round_tf32(b.kernel[((size_t)t * b.ic + c) * b.oc + d]);
                 CK(cudaMalloc(&b.d_wpack, n * 4));
                 CK(cudaMemcpy(b.d_wpack, pk.data(), n * 4, cudaMemcpyHostToDevice));
             }
             if (encode_map_b(b)) return 1;
+            if (b.up.splits > 1) {
+                const size_t ws = (size_t)b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
+                const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
+                CK(cudaMalloc(&b.d_workspace, ws));
+                CK(cudaMalloc(&b.d_counters, nc));
+                CK(cudaMemset(b.d_workspace, 0, ws));
+                CK(cudaMemset(b.d_counters, 0, nc));
+            }
         }
         net->launches += 1 + (b.pool_separate ? 1 : 0);
         in_bf16 = b.out_bf16;
@@ -1235,6 +1274,8 @@ int dnnb_net_destroy(dnnb_net *net) {
         if (b.d_out) cudaFree(b.d_out);
         if (b.d_kernel) cudaFree(b.d_kernel);
         if (b.d_wpack) cudaFree(b.d_wpack);
+        if (b.d_workspace) cudaFree(b.d_workspace);
+        if (b.d_counters) cudaFree(b.d_counters);
         if (b.d_scale) cudaFree(b.d_scale);
         if (b.d_shift) cudaFree(b.d_shift);
     }

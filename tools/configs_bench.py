@@ -96,15 +96,20 @@ def main():
     doc = {"peaks": peaks, "tensor_peak_tflops": {}}
     for prec in ("tf32", "bf16"):
         doc["tensor_peak_tflops"][prec] = max(_lib.measure_mma_peak(prec) for _ in range(3))
-    # configs[1]: batch-1 latency
+    # configs[1]: batch-1 latency, default (deterministic) plan and DNNB_LATENCY_MODE=1 (split-K with atomics)
     doc["batch1_latency"] = {}
-    for prec in ("tf32", "bf16"):
-        net = make_net(1, prec)
-        ts = device_forward_times(net, 1, args.forwards)
-        doc["batch1_latency"][prec] = {"median_us": round(statistics.median(ts) * 1e3, 2), "min_us": round(min(ts) * 1e3, 2),
-                                       "p90_us": round(sorted(ts)[int(0.9 * len(ts))] * 1e3, 2), "forwards": len(ts),
-                                       "layers": layer_table(net, 1, prec, peaks, doc["tensor_peak_tflops"][prec])}
-        net.close()
+    for mode in ("default", "latency_mode"):
+        if mode == "latency_mode":
+            os.environ["DNNB_LATENCY_MODE"] = "1"
+        for prec in ("tf32", "bf16"):
+            net = make_net(1, prec)
+            ts = device_forward_times(net, 1, args.forwards)
+            doc["batch1_latency"][prec + "_" + mode] = {
+                "median_us": round(statistics.median(ts) * 1e3, 2), "min_us": round(min(ts) * 1e3, 2),
+                "p90_us": round(sorted(ts)[int(0.9 * len(ts))] * 1e3, 2), "forwards": len(ts),
+                "layers": layer_table(net, 1, prec, peaks, doc["tensor_peak_tflops"][prec])}
+            net.close()
+    os.environ.pop("DNNB_LATENCY_MODE", None)
     # configs[2] and the per-layer table at batch 256
     doc["batch256"] = {}
     for prec in ("tf32", "bf16"):
