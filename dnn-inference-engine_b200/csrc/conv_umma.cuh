@@ -51,12 +51,16 @@ struct Params {
     int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
     float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
     // split-K (small batches: too few output tiles to fill the SMs, weights dominate the traffic):
-    // `splits` CTAs share one output tile, each reduces a slice of K into `workspace` with vector
-    // atomics; the CTA that arrives last at `counters[tile]` runs the epilogue from the workspace
-    // and leaves workspace and counter zeroed for the next launch.
+    // `splits` CTAs share one output tile.  Each stores the partial sums of its K slice to its own
+    // slab of `workspace`, bumps `counters[tile]` and waits until all `splits` slabs are there; then
+    // every CTA sums a 1/splits share of the tile's rows over the slabs IN SLAB ORDER and runs the
+    // epilogue on it: deterministic, no atomics on data.  All CTAs of the launch must be co-resident
+    // (grid = work items <= SMs, cooperative launch).  Counters only ever grow: launch number g waits
+    // for g * splits.
     int splits;           // 1 = off
-    float *workspace;     // [num_m_tiles * MT * 128][num_n_tiles * BN] fp32, zero between launches
-    int *counters;        // [num_m_tiles * num_n_tiles], zero between launches
+    float *workspace;     // [splits][num_m_tiles * MT * 128][num_n_tiles * BN] fp32
+    int *counters;        // [num_m_tiles * num_n_tiles]
+    int split_target;     // launch number * splits
 };
 
 // MT = M tiles (of 128 rows) per CTA tile that share every B tile: MT = 2 turns the CTA tile
@@ -103,7 +107,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t *tail = smem + STAGES * C::STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail);           // full[S], empty[S], tfull[2], tempty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
-    volatile int *s_flag = reinterpret_cast<volatile int *>(tail + 520);   // split-K: "this CTA finishes the tile"
     float *s_scale = reinterpret_cast<float *>(tail + 1024);
     float *s_shift = s_scale + 1024;
     float *s_out = s_shift + 1024;       // STAGE_OUT only: [4 warps][32 rows][OC]
@@ -260,21 +263,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const bool split_k = p.splits > 1;
             const int ldw = p.num_n_tiles * BN;
             if (split_k) {
-                // phase 1: add this K slice's partial sums to the workspace, free the accumulator
+                const int split = tile / tiles_mn;
+                const size_t slab = (size_t)p.num_m_tiles * MT * kBM * ldw;       // floats per K-slice slab
+                // phase 1: this K slice's partial sums -> own slab; free the accumulator
 #pragma unroll 1
                 for (int mi = 0; mi < MT; ++mi) {
-                    float *wrow = p.workspace + ((size_t)(m_tile * MT + mi) * kBM + row) * ldw + n_tile * BN;
+                    float4 *wrow = reinterpret_cast<float4 *>(p.workspace + split * slab +
+                                                              ((size_t)(m_tile * MT + mi) * kBM + row) * ldw + n_tile * BN);
 #pragma unroll 1
                     for (int chunk = 0; chunk < BN / 32; ++chunk) {
                         uint32_t raw[32];
                         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
                         ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + chunk * 32 + j),
-                                         "f"(__uint_as_float(raw[j])), "f"(__uint_as_float(raw[j + 1])),
-                                         "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
-                                         : "memory");
+                        for (int j = 0; j < 8; ++j)
+                            __stcg(wrow + chunk * 8 + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                                      __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
                     }
                 }
                 ptx::tc_fence_before();
@@ -282,15 +286,62 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (row == 0) {
-                    const int prev = atomicAdd(p.counters + (tile % tiles_mn), 1);
-                    *s_flag = prev == p.splits - 1 ? 1 : 0;
-                    if (prev == p.splits - 1) p.counters[tile % tiles_mn] = 0;     // leave it ready for the next launch
+                    int *ctr = p.counters + (tile % tiles_mn);
+                    atomicAdd(ctr, 1);
+                    long long t0 = clock64();
+                    while (true) {                  // every sibling CTA is resident (cooperative launch): this terminates
+                        int seen;
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+                        if (seen >= p.split_target) break;
+                        __nanosleep(64);
+                        if (clock64() - t0 > 4000000000LL) __trap();
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                const bool last = *s_flag != 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");    // s_flag may be rewritten by the next work item
-                if (!last) continue;
                 __threadfence();
+                // phase 2: rows [r0, r1) of the tile are this CTA's share: sum the slabs in order, finish, store
+                const int tile_rows = MT * kBM;
+                const int rows_per = (tile_rows + p.splits - 1) / p.splits;
+                const int r0 = split * rows_per;
+                const int r1 = r0 + rows_per < tile_rows ? r0 + rows_per : tile_rows;
+                constexpr int C4 = BN / 4;
+                for (int u = row; u < (r1 - r0) * C4; u += 128) {
+                    const int rr = r0 + u / C4, c4 = u - (u / C4) * C4;
+                    const int m = m_tile * tile_rows + rr;                 // output pixel (im2col: linear index)
+                    if (m >= p.M_total) continue;
+                    const float4 *src = reinterpret_cast<const float4 *>(p.workspace + ((size_t)m_tile * tile_rows + rr) * ldw +
+                                                                          n_tile * BN) + c4;
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sidx = 0; sidx < p.splits; ++sidx) {
+                        const float4 t4 = __ldcg(src + sidx * (slab / 4));
+                        sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
+                    }
+                    const int col = n_tile * BN + c4 * 4;
+                    float v4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
+                        if (p.leaky) y = fmaxf(y, 0.1f * y);
+                        if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                        else if (p.round_tf32) y = ptx::round_tf32(y);
+                        v4[e] = y;
+                    }
+                    if constexpr (OUT_BF16) {
+                        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
+                    } else {
+                        float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                        if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < p.OC) o[e] = v4[e];
+                        }
+                    }
+                }
+                continue;
             }
 
 #pragma unroll 1
@@ -319,21 +370,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll 1
             for (int chunk = 0; chunk < BN / 32; ++chunk) {
                 uint32_t raw[32];
-                if (split_k) {
-                    // phase 2 (last CTA of the tile): the sums now live in the workspace; read and clear it
-                    float4 *wsrc = reinterpret_cast<float4 *>(p.workspace + ((size_t)(m_tile * MT + mi) * kBM + row) * ldw +
-                                                              n_tile * BN + chunk * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 t4 = __ldcg(wsrc + j);
-                        raw[4 * j] = __float_as_uint(t4.x); raw[4 * j + 1] = __float_as_uint(t4.y);
-                        raw[4 * j + 2] = __float_as_uint(t4.z); raw[4 * j + 3] = __float_as_uint(t4.w);
-                        __stcg(wsrc + j, make_float4(0.f, 0.f, 0.f, 0.f));
-                    }
-                } else {
-                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
-                    ptx::tmem_ld_wait();
-                }
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
+                ptx::tmem_ld_wait();
                 const int col0 = n_tile * BN + chunk * 32;
                 float v[32];
 #pragma unroll
@@ -469,10 +507,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
             }
             }   // mi
-            if (!split_k) {
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(bar_tempty + 8 * acc);
-            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tempty + 8 * acc);
         }
     }
 

@@ -148,6 +148,20 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
+    if (grid < 0) {
+        // split-K: sibling CTAs wait for one another, so the whole grid must be resident: cooperative launch
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)-grid);
+        cfg.blockDim = dim3(umma_conv::kThreads);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
+    }
     kern<<<grid, umma_conv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);
     return cudaGetLastError();
 }
@@ -275,8 +289,9 @@ struct Block {
     float *d_kernel = nullptr;                  // HWIO fp32 (SIMT)
     void *d_wpack = nullptr;                    // [tap][OCp][IC] tf32-rounded fp32 or bf16
     float *d_scale = nullptr, *d_shift = nullptr;
-    float *d_workspace = nullptr;               // split-K partial sums (zero between launches)
-    int *d_counters = nullptr;                  // split-K arrival counters (zero between launches)
+    float *d_workspace = nullptr;               // split-K partial sums, one slab per K slice
+    int *d_counters = nullptr;                  // split-K arrival counters (monotonic)
+    int split_gen = 0;                          // launches so far: launch g waits for g * splits arrivals
     void *d_conv_out = nullptr;                 // conv(+fused pool) output
     void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
     size_t conv_out_elems = 0, out_elems = 0;
@@ -384,10 +399,10 @@ int encode_map_b(Block &b) {
     return 0;
 }
 
-// DNNB_LATENCY_MODE=1 (read when a network is finalized) trades two properties for small-batch
-// latency: split-K sums partial tiles with floating-point atomics, so results are no longer
-// bit-reproducible run to run nor identical across batch sizes (they stay within fp32 reordering
-// noise, ~1e-6 relative); default off.
+// DNNB_LATENCY_MODE=1 (read when a network is finalized) plans for small-batch latency: split-K over
+// co-resident CTAs (deterministic: partial sums are added in slice order) and im2col tiles instead of
+// mostly-padding spatial tiles.  Results are reproducible run to run but, because the K sum is cut
+// differently, not bit-identical to the default plan (fp32 reordering noise); default off.
 bool latency_mode() {
     const char *v = getenv("DNNB_LATENCY_MODE");
     return v && v[0] == '1';
@@ -534,12 +549,12 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
                 const int kstages = total_kb / kbs;
                 p.splits = 1;
-                if (tiles_mn * 2 <= net->num_sms && kstages >= 8 && latency_mode()) {
+                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && latency_mode()) {
                     int sp = net->num_sms / tiles_mn;
                     if (sp > kstages / 4) sp = kstages / 4;
                     if (sp >= 2) p.splits = sp;
                 }
-                const int tiles = tiles_mn * p.splits;
+                const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;
             }
         }
@@ -636,7 +651,14 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         umma_conv::Params p = b.up;
         p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
         p.workspace = b.d_workspace; p.counters = b.d_counters;
-        CK(b.umma->launch(b.map_a, b.map_b, p, b.grid, st));
+        if (p.splits > 1) {
+            if (b.split_gen >= (1 << 24)) {       // keep the monotonic counters far from overflow
+                CK(cudaMemsetAsync(b.d_counters, 0, (size_t)p.num_m_tiles * p.num_n_tiles * sizeof(int), st));
+                b.split_gen = 0;
+            }
+            p.split_target = ++b.split_gen * p.splits;
+        }
+        CK(b.umma->launch(b.map_a, b.map_b, p, p.splits > 1 ? -b.grid : b.grid, st));
     }
     if (b.pool_separate) {
         simt::PoolParams q{};
@@ -971,7 +993,7 @@ int dnnb_net_finalize(dnnb_net *net) {
             }
             if (encode_map_b(b)) return 1;
             if (b.up.splits > 1) {
-                const size_t ws = (size_t)b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
+                const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
                 const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
                 CK(cudaMalloc(&b.d_workspace, ws));
                 CK(cudaMalloc(&b.d_counters, nc));

@@ -275,8 +275,8 @@ def test_full_size_batch256_properties(oracle_libs):
 
 
 def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeypatch):
-    """DNNB_LATENCY_MODE=1: split-K with fp32 atomics for small batches.  Not bit-reproducible by design;
-    must agree with the default (deterministic) engine to fp32 reordering noise and with the reference."""
+    """DNNB_LATENCY_MODE=1: split-K over co-resident CTAs for small batches.  Reproducible run to run
+    (slices are summed in order); not bit-identical to the default plan, whose K sum is cut differently."""
     x = make_images(1, seed=100)
     base = _yolo_engine(1, "tf32")
     ref = base.run(x).copy()
@@ -289,7 +289,8 @@ def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeyp
     gold = np.load(os.path.join(GOLDEN, "yolo_w0_i100.npz"))["out_openblas"]
     # a re-ordered fp32 sum can flip a TF32 rounding of an activation (2^-11 relative), which then propagates:
     # the two engines differ by about as much as either differs from the reference
-    assert normalised_error(out, ref) < 2e-3 and normalised_error(out2, out) < 2e-3
+    np.testing.assert_array_equal(out2, out)
+    assert normalised_error(out, ref) < 2e-3
     assert normalised_error(out, gold) < TOL["tf32"]
 
 
