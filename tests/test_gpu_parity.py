@@ -274,6 +274,26 @@ def test_full_size_batch256_properties(oracle_libs):
     eng.close(); eng1.close()
 
 
+@pytest.mark.parametrize("hw,batch", [(320, 2), (352, 1), (96, 3)])
+def test_other_input_sizes(oracle_libs, hw, batch):
+    """Nothing in the kernels is tied to 416: the YOLOv2-tiny stack on other multiples of 32."""
+    weights = make_weights(2)
+    x = make_images(batch, seed=300, hw=hw)
+    g = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g, [batch, hw, hw, 3], weights)
+    eng = dnn_b200.DnnInferenceEngine(g, False, precision="tf32")
+    out = eng.run(x)
+    plan = [p["kernel"] for p in eng.kernel_plan()]
+    c = chain.Chain("oracle"); build_yolov2tiny(c, x.shape, weights)
+    ref = c.run(x)
+    assert out.shape == ref.shape == (batch, hw // 32, hw // 32, 125)
+    err = normalised_error(out, ref)
+    print("hw %d: err=%.3g plan=%s" % (hw, err, plan))
+    assert err < TOL["tf32"]
+    assert all(k.startswith("umma") for k in plan)
+    eng.close()
+
+
 def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeypatch):
     """DNNB_LATENCY_MODE=1: split-K over co-resident CTAs for small batches.  Reproducible run to run
     (slices are summed in order); not bit-identical to the default plan, whose K sum is cut differently."""
