@@ -294,6 +294,49 @@ def test_other_input_sizes(oracle_libs, hw, batch):
     eng.close()
 
 
+def test_batch_sharding_over_two_gpus_equals_one_gpu():
+    """the G-GPU run is bit-identical to the 1-GPU run of the same build on the same inputs."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import sharded
+    weights = make_weights(0)
+    spec = []
+    for i, w in enumerate(weights):
+        blk = {"kernel": w["kernel"], "padding": "SAME", "biases": w["biases"]}
+        if "gamma" in w:
+            blk.update(mean=w["moving_mean"], variance=w["moving_variance"], gamma=w["gamma"], epsilon=1e-5, leaky=True)
+        blk["pool"] = None if POOLS[i] is None else (POOLS[i][0], POOLS[i][1], "SAME")
+        spec.append(blk)
+    total = 7                                           # ragged: shards of 4 and 3 images
+    x = make_images(total, seed=400)
+    one = _lib.Net(x.shape, spec, precision="tf32", device=0)
+    ref = one.forward(x)
+    eng = sharded.MultiGpuEngine(lambda dev, b: _lib.Net((b, 416, 416, 3), spec, precision="tf32", device=dev), total, [0, 1])
+    hin, hout = _lib.PinnedArray(x.shape), _lib.PinnedArray(ref.shape)
+    hin.array[...] = x
+    out = eng.run(hin.array, hout.array)
+    np.testing.assert_array_equal(out, ref)
+    eng.close(); one.close(); hin.free(); hout.free()
+
+
+def test_valid_padding_and_odd_pool_take_the_cuda_core_path(oracle_libs):
+    """A block the tcgen05 kernels do not cover (VALID conv, odd sizes, 3x3/2 pool) still runs on the GPU."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((2, 15, 17, 6)).astype(np.float32)
+    k = rng.standard_normal((3, 3, 6, 10)).astype(np.float32)
+    b = rng.standard_normal(10).astype(np.float32)
+    net = _lib.Net(x.shape, [{"kernel": k, "padding": 'VALID', "biases": b, "leaky": True, "pool": (3, 2, 'VALID')}], precision="tf32")
+    assert net.block_info(0)["kernel"] == "simt"
+    c = chain.Chain("oracle")
+    cur = c.create_conv2d(c.create_input(x.shape), k, [1, 1, 1, 1], 'VALID')
+    cur = c.create_leaky_relu(c.create_bias_add(cur, b))
+    c.create_max_pool2d(cur, [1, 3, 3, 1], [1, 2, 2, 1], 'VALID')
+    ref = c.run(x)
+    got = net.forward(x)
+    assert got.shape == ref.shape and normalised_error(got, ref) < 1e-5
+    net.close()
+
+
 def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeypatch):
     """DNNB_LATENCY_MODE=1: split-K over co-resident CTAs for small batches.  Reproducible run to run
     (slices are summed in order); not bit-identical to the default plan, whose K sum is cut differently."""
