@@ -145,14 +145,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         // ------------------------------------------------------------ patch producers
         // 340 groups of 4 pixels per patch; thread handles groups tid, tid + 256.  The group ->
         // (patch row, column group) split does not depend on the tile: hoist it.
-        int g_row[kRounds], g_src[kRounds], g_dst[kRounds], g_px[kRounds];
+        int g_row[kRounds], g_dst[kRounds], g_px[kRounds];
 #pragma unroll
         for (int it = 0; it < kRounds; ++it) {
             const int g = threadIdx.x + kProducerWarps * 32 * it;
             const int r = g / kGroups, gx = g - r * kGroups;
             g_row[it] = g < kTileGroups ? r : 1 << 20;              // invalid groups fail the row test below
             g_px[it] = 4 * gx - 4;
-            g_src[it] = (r * p.W + 4 * gx - 4) * 3;
             g_dst[it] = r * kPatchRowBytes + gx * 64;
         }
         Coord tc = decode(tile_begin);

@@ -9,10 +9,13 @@
 // at any row of a TMA-written slab (tools/probe_desc.cu, Q1/Q2).  The 3x3xICxOC weights stay
 // resident in shared memory for the whole kernel.
 //
-// Tile = output rows (2j, 2j+1) x 128 columns.  TMEM columns [0,OC) hold output row 2j and
-// [OC,2OC) row 2j+1; patch row r is multiplied once by the stacked weights
-// [W(di=r) | W(di=r-1)] (N = 2*OC; N = OC for r = 0 and r = 3).  The epilogue thread of lane m
-// holds both rows of pixel column m: vertical max in registers, horizontal max by one shuffle.
+// Tile = TR output rows x 128 columns (TR = 2, 4 or 8: as many as shared memory and TMEM allow;
+// taller tiles read each patch row from shared memory fewer times per output pixel and amortise
+// the per-tile handshakes).  TMEM columns [OC o, OC o + OC) hold output row o of the tile; patch
+// row r feeds the output rows o = r - di, so it is multiplied once by the stacked weights
+// [W(di=2) | W(di=1) | W(di=0)] (N = 3 OC, clipped at the tile's top and bottom) into the columns
+// starting at OC max(0, r-2).  The epilogue thread of lane m holds every row of pixel column m:
+// vertical max in registers, horizontal max by one shuffle.
 //
 // CTA = 352 threads: warp 0 TMA producer, warps 1-2 MMA issuers (alternate tiles; warp 1 owns TMEM),
 // 2 x 4 epilogue warps that alternate tiles.  One channel chunk only: IC * elem_size must equal the swizzle span (32/64/128 B).
@@ -28,12 +31,11 @@ namespace rowpair {
 constexpr int kMmaWarps = 2;      // tiles alternate between two issuing warps: the MMAs are small, issue-bound
 constexpr int kThreads = (1 + kMmaWarps + 8) * 32;
 constexpr int kPatchW = 130;      // 128 columns + left/right halo
-constexpr int kPatchRows = 4;     // 2 output rows + top/bottom halo
 
 struct Params {
     int B, H, W;          // conv output = input spatial size
     int col_tiles;        // ceil(W / 128)
-    int num_tiles;        // B * (H/2) * col_tiles
+    int num_tiles;        // B * (H/TR) * col_tiles
     const float *scale;   // [OC]
     const float *shift;   // [OC]
     void *out;            // [B, H/2, W/2, OC]
@@ -45,19 +47,21 @@ struct Params {
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
 
-template <int OC, int SWZ>
+template <int OC, int SWZ, int TR>
 struct Cfg {
+    static constexpr int PATCH_ROWS = TR + 2;                  // output rows + top/bottom halo
     static constexpr int PATCH_ROW = kPatchW * SWZ;
-    static constexpr int PATCH_RAW = kPatchRows * PATCH_ROW;
+    static constexpr int PATCH_RAW = PATCH_ROWS * PATCH_ROW;
     static constexpr int PATCH_BYTES = (PATCH_RAW + 1023) / 1024 * 1024;
     static constexpr int W_DJ_BYTES = 3 * OC * SWZ;            // one dj: rows [di=2 | di=1 | di=0] x OC
     static constexpr int W_BYTES = 3 * W_DJ_BYTES;
     static constexpr int TAIL_BYTES = 1024 + 2 * OC * 4;
     static constexpr int BUDGET = 227 * 1024 - 1024;
-    static constexpr int STAGES = cmin(4, (BUDGET - W_BYTES - TAIL_BYTES) / PATCH_BYTES);
+    static constexpr int STAGES = cmin(4, (BUDGET - W_BYTES - TAIL_BYTES) / PATCH_BYTES) / kMmaWarps * kMmaWarps;
     static constexpr int SMEM_BYTES = STAGES * PATCH_BYTES + W_BYTES + TAIL_BYTES + 1024;
-    static constexpr int ACC_COLS = 2 * OC;
+    static constexpr int ACC_COLS = TR * OC;
     static constexpr int ACC_STAGES = cmin(4, 512 / ACC_COLS);
+    static_assert(TR % 2 == 0 && 3 * OC <= 256, "whole pooling row pairs; N = 3*OC must be one MMA");
     static constexpr int TMEM_COLS = pow2_at_least(ACC_COLS * ACC_STAGES);
     static_assert(STAGES >= 2, "need two patch stages");
     // one owner per ring slot (see conv0_umma.cuh): stages and accumulators never change their MMA warp
@@ -67,11 +71,11 @@ struct Cfg {
     static_assert(OC % 16 == 0 && 3 * OC <= 256, "weights of one dj must fit one TMA box");
 };
 
-template <bool BF16, bool OUT_BF16, int OC, int SWZ>
+template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                     const Params p) {
-    using C = Cfg<OC, SWZ>;
+    using C = Cfg<OC, SWZ, TR>;
     constexpr int STAGES = C::STAGES, ACC = C::ACC_STAGES;
     constexpr int KC = SWZ / 32;                     // MMAs along K per tap (32 bytes of K each)
 
@@ -93,7 +97,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t bar_w = bar_tempty + 8 * ACC;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rows2 = p.H >> 1;
+    const int rows2 = p.H / TR;          // row tiles per image
     // a CTA owns a contiguous range of tiles; (column tile, row pair, image) advance incrementally
     const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_begin = (int)blockIdx.x * per_cta;
@@ -140,14 +144,13 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 ptx::mbar_wait(bar_empty + 8 * stage, ((t / STAGES) & 1) ^ 1);
                 ptx::mbar_expect_tx(bar_full + 8 * stage, C::PATCH_RAW);
                 ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, tc.ct * 128 - 1,
-                                 2 * tc.j - 1, tc.n);
+                                 TR * tc.j - 1, tc.n);
             }
         }
     } else if (warp <= kMmaWarps) {
         // ------------------------------------------------------------ MMA issuers
         if (ptx::elect_one()) {
             constexpr uint32_t fmt = BF16 ? 1u : 2u;
-            constexpr uint32_t idesc_wide = ptx::umma_idesc(fmt, 2 * OC), idesc_narrow = ptx::umma_idesc(fmt, OC);
             constexpr uint32_t HI = ptx::umma_desc_hi(SWZ);
             const uint32_t b_lo0 = ptx::umma_desc_lo(w_base);
             ptx::mbar_wait(bar_w, 0);
@@ -158,17 +161,23 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 ptx::tc_fence_after();
                 const uint32_t a_lo0 = ptx::umma_desc_lo(patch_base + stage * C::PATCH_BYTES);
                 const uint32_t d = tmem_base + acc * C::ACC_COLS;
-                // weight rows of one dj slab: [W(di=2) | W(di=1) | W(di=0)], OC rows each.
-                //   r=1: rows OC..3OC   = [W1|W0] -> cols [0,2OC)      r=2: rows 0..2OC = [W2|W1] -> cols [0,2OC)
-                //   r=0: rows 2OC..3OC  =  W0     -> cols [0,OC)       r=3: rows 0..OC  =  W2     -> cols [OC,2OC)
-                // r=1 first: its N = 2*OC MMA initialises every accumulator column.
+                // Weight rows of one dj slab: [W(di=2) | W(di=1) | W(di=0)], OC rows each.  Patch row r feeds
+                // output rows o in [max(0, r-2), min(TR-1, r)] with di = r - o: operand rows from
+                // OC (2 - (r - o_lo)), N = OC (#rows), accumulator columns from OC o_lo.
+                // Rows 2, 5, 8, ... go first: together they touch every column exactly once and initialise it.
                 // Every descriptor is (per-tile base) + (compile-time constant), in 16-byte units.
+                constexpr int NINIT = (TR + 2) / 3;                  // rows 2, 5, ... <= TR + 1
 #pragma unroll
-                for (int oi = 0; oi < 4; ++oi) {
-                    const int r = oi == 0 ? 1 : oi == 1 ? 2 : oi == 2 ? 0 : 3;
-                    const int wrow = r == 0 ? 2 * OC : r == 1 ? OC : 0;
-                    const bool wide = r == 1 || r == 2;
-                    const uint32_t dcol = d + (r == 3 ? OC : 0);
+                for (int oi = 0; oi < C::PATCH_ROWS; ++oi) {
+                    int r;
+                    if (oi < NINIT) r = 2 + 3 * oi;
+                    else { const int q = oi - NINIT; r = q + q / 2; }   // the remaining rows 0,1,3,4,6,7,9,...
+                    const int o_lo = r - 2 > 0 ? r - 2 : 0;
+                    const int o_hi = r < TR - 1 ? r : TR - 1;
+                    const int n = OC * (o_hi - o_lo + 1);
+                    const int wrow = OC * (2 - (r - o_lo));
+                    const uint32_t idesc = ptx::umma_idesc(fmt, n);
+                    const uint32_t dcol = d + OC * o_lo;
 #pragma unroll
                     for (int dj = 0; dj < 3; ++dj) {
 #pragma unroll
@@ -176,7 +185,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             const uint32_t a_off = ((r * kPatchW + dj) * SWZ + 32 * k) >> 4;
                             const uint32_t b_off = (dj * C::W_DJ_BYTES + wrow * SWZ + 32 * k) >> 4;
                             ptx::umma<BF16>(dcol, ptx::umma_desc_join(a_lo0 + a_off, HI), ptx::umma_desc_join(b_lo0 + b_off, HI),
-                                            wide ? idesc_wide : idesc_narrow, (oi | dj | k) != 0 ? 1u : 0u);
+                                            idesc, (oi >= NINIT || dj != 0 || k != 0) ? 1u : 0u);
                         }
                     }
                 }
@@ -199,13 +208,16 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
             ptx::tc_fence_after();
             if (ct * 128 + quarter * 32 < p.W) {           // warp-uniform: skip quarters right of the image
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS;
-                const size_t pix = ((size_t)n * rows2 + j) * OW + (w >> 1);
+#pragma unroll 1
+                for (int rp = 0; rp < TR / 2; ++rp) {                  // pooling row pairs of the tile
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + 2 * rp * OC;
+                const int orow = TR * j + 2 * rp;                      // conv output row of the pair's first row
+                const size_t pix = ((size_t)n * (p.H >> 1) + (orow >> 1)) * OW + (w >> 1);
 #pragma unroll 1
                 for (int c0 = 0; c0 < OC; c0 += 16) {
                     uint32_t top[16], bot[16];
-                    ptx::tmem_ld_32x16(taddr + c0, top);         // output row 2j
-                    ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // output row 2j+1
+                    ptx::tmem_ld_32x16(taddr + c0, top);         // first row of the pair
+                    ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // second row
                     ptx::tmem_ld_wait();
                     float v[16];
                     if (p.prepool != nullptr && w < p.W) {     // debug dump of the pooled-over activations (cold path)
@@ -216,8 +228,8 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
                             if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
                             else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
-                            p.prepool[(((size_t)n * p.H + 2 * j) * p.W + w) * OC + c0 + c] = a;
-                            p.prepool[(((size_t)n * p.H + 2 * j + 1) * p.W + w) * OC + c0 + c] = b;
+                            p.prepool[(((size_t)n * p.H + orow) * p.W + w) * OC + c0 + c] = a;
+                            p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * OC + c0 + c] = b;
                         }
                     }
                     float r8[8];
@@ -277,6 +289,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                 }
+                }   // rp
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);

@@ -346,166 +346,166 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 #pragma unroll 1
             for (int mi = 0; mi < MT; ++mi) {
-            bool valid;
-            size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
-            size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
-            if constexpr (IM2COL) {
-                const int m = (m_tile * MT + mi) * kBM + row;
-                valid = m < p.M_total;
-                out_pix = (size_t)m;
-            } else {
-                const int w0 = (m_tile % p.tiles_w) * p.tw;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + mi) * p.nb;
-                const int wl = row & (p.tw - 1);
-                const int hl = (row >> p.log2_tw) & (p.th - 1);
-                const int nl = row >> (p.log2_tw + p.log2_th);
-                const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
-                valid = n < p.B;
-                if constexpr (POOL) out_pix = ((size_t)n * p.OH + (h >> 1)) * p.OW + (w >> 1);
-                else out_pix = ((size_t)n * p.OH + h) * p.OW + w;
-                pre_pix = ((size_t)n * p.H + h) * p.W + w;
-            }
+                bool valid;
+                size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
+                size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
+                if constexpr (IM2COL) {
+                    const int m = (m_tile * MT + mi) * kBM + row;
+                    valid = m < p.M_total;
+                    out_pix = (size_t)m;
+                } else {
+                    const int w0 = (m_tile % p.tiles_w) * p.tw;
+                    const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                    const int n0 = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + mi) * p.nb;
+                    const int wl = row & (p.tw - 1);
+                    const int hl = (row >> p.log2_tw) & (p.th - 1);
+                    const int nl = row >> (p.log2_tw + p.log2_th);
+                    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+                    valid = n < p.B;
+                    if constexpr (POOL) out_pix = ((size_t)n * p.OH + (h >> 1)) * p.OW + (w >> 1);
+                    else out_pix = ((size_t)n * p.OH + h) * p.OW + w;
+                    pre_pix = ((size_t)n * p.H + h) * p.W + w;
+                }
 
 #pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                uint32_t raw[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
-                ptx::tmem_ld_wait();
-                const int col0 = n_tile * BN + chunk * 32;
-                float v[32];
+                for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                    uint32_t raw[32];
+                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
+                    ptx::tmem_ld_wait();
+                    const int col0 = n_tile * BN + chunk * 32;
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
-                    const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j);
-                    v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
-                    v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
-                    v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
-                    v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
-                }
-                if (p.leaky) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
-                }
-                if constexpr (!OUT_BF16) {
-                    if (p.round_tf32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
+                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j);
+                        v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
+                        v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
+                        v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
+                        v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
                     }
-                } else {   // round before pooling: the reference pools the stored values
+                    if (p.leaky) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-                }
-
-                if constexpr (POOL) {
-                    if (p.prepool != nullptr && valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.OC) p.prepool[pre_pix * p.OC + col0 + j] = v[j];
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
                     }
-                    // butterfly 2x2 max over lanes (w^1, then h^1 = lane ^ tw); each lane ends up
-                    // with 8 of the 32 columns of its window: 16*(w&1) + 8*(h&1) + [0,8)
-                    const bool wodd = lane & 1;
-                    float a[16];
+                    if constexpr (!OUT_BF16) {
+                        if (p.round_tf32) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float keep = wodd ? v[16 + j] : v[j];
-                        const float send = wodd ? v[j] : v[16 + j];
-                        a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                    }
-                    const bool hodd = (lane >> p.log2_tw) & 1;
-                    float r8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float keep = hodd ? a[8 + j] : a[j];
-                        const float send = hodd ? a[j] : a[8 + j];
-                        r8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tw));
-                    }
-                    const int col = col0 + (wodd ? 16 : 0) + (hodd ? 8 : 0);
-                    if (valid && col < p.OC) {
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col;
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]);
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(r8[2], r8[3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]);
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(r8[6], r8[7]);
-                            pk.x = *reinterpret_cast<uint32_t *>(&t0);
-                            pk.y = *reinterpret_cast<uint32_t *>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&t2);
-                            pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                            *reinterpret_cast<uint4 *>(o) = pk;
-                        } else {
-                            float *o = static_cast<float *>(p.out) + out_pix * p.OC + col;
-                            *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
-                            *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+                            for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
                         }
+                    } else {   // round before pooling: the reference pools the stored values
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
                     }
-                } else {
-                    if (valid) {
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col0;
-                            if ((p.OC & 7) == 0) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    if (col0 + j < p.OC) {
-                                        uint4 pk;
-                                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                                        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                                        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                                        pk.x = *reinterpret_cast<uint32_t *>(&t0);
-                                        pk.y = *reinterpret_cast<uint32_t *>(&t1);
-                                        pk.z = *reinterpret_cast<uint32_t *>(&t2);
-                                        pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                                        *reinterpret_cast<uint4 *>(o + j) = pk;
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < p.OC) o[j] = __float2bfloat16_rn(v[j]);
-                            }
-                        } else if constexpr (STAGE_OUT) {
-                            float *so = s_out + (size_t)(quarter * 32 + lane) * p.OC + col0;
+
+                    if constexpr (POOL) {
+                        if (p.prepool != nullptr && valid) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.OC) so[j] = v[j];
-                        } else {
-                            float *o = static_cast<float *>(p.out) + out_pix * p.OC + col0;
-                            if ((p.OC & 3) == 0) {
+                                if (col0 + j < p.OC) p.prepool[pre_pix * p.OC + col0 + j] = v[j];
+                        }
+                        // butterfly 2x2 max over lanes (w^1, then h^1 = lane ^ tw); each lane ends up
+                        // with 8 of the 32 columns of its window: 16*(w&1) + 8*(h&1) + [0,8)
+                        const bool wodd = lane & 1;
+                        float a[16];
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4)
-                                    if (col0 + j < p.OC)
-                                        *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 16; ++j) {
+                            const float keep = wodd ? v[16 + j] : v[j];
+                            const float send = wodd ? v[j] : v[16 + j];
+                            a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        }
+                        const bool hodd = (lane >> p.log2_tw) & 1;
+                        float r8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float keep = hodd ? a[8 + j] : a[j];
+                            const float send = hodd ? a[j] : a[8 + j];
+                            r8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tw));
+                        }
+                        const int col = col0 + (wodd ? 16 : 0) + (hodd ? 8 : 0);
+                        if (valid && col < p.OC) {
+                            if constexpr (OUT_BF16) {
+                                __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col;
+                                uint4 pk;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]);
+                                __nv_bfloat162 t1 = __floats2bfloat162_rn(r8[2], r8[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]);
+                                __nv_bfloat162 t3 = __floats2bfloat162_rn(r8[6], r8[7]);
+                                pk.x = *reinterpret_cast<uint32_t *>(&t0);
+                                pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t *>(&t2);
+                                pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                                *reinterpret_cast<uint4 *>(o) = pk;
                             } else {
+                                float *o = static_cast<float *>(p.out) + out_pix * p.OC + col;
+                                *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+                                *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+                            }
+                        }
+                    } else {
+                        if (valid) {
+                            if constexpr (OUT_BF16) {
+                                __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col0;
+                                if ((p.OC & 7) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 8) {
+                                        if (col0 + j < p.OC) {
+                                            uint4 pk;
+                                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                                            pk.x = *reinterpret_cast<uint32_t *>(&t0);
+                                            pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                                            pk.z = *reinterpret_cast<uint32_t *>(&t2);
+                                            pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                                            *reinterpret_cast<uint4 *>(o + j) = pk;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (col0 + j < p.OC) o[j] = __float2bfloat16_rn(v[j]);
+                                }
+                            } else if constexpr (STAGE_OUT) {
+                                float *so = s_out + (size_t)(quarter * 32 + lane) * p.OC + col0;
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < p.OC) o[j] = v[j];
+                                    if (col0 + j < p.OC) so[j] = v[j];
+                            } else {
+                                float *o = static_cast<float *>(p.out) + out_pix * p.OC + col0;
+                                if ((p.OC & 3) == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4)
+                                        if (col0 + j < p.OC)
+                                            *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (col0 + j < p.OC) o[j] = v[j];
+                                }
                             }
                         }
                     }
                 }
-            }
-            if constexpr (STAGE_OUT) {
-                // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
-                __syncwarp();
-                const int row0 = m_tile * kBM + quarter * 32;
-                const int rows = min(32, p.M_total - row0);
-                if (rows > 0) {
-                    const int count = rows * p.OC;
-                    const float *src = s_out + (size_t)quarter * 32 * p.OC;
-                    float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
-                    if ((((size_t)quarter * 32 * p.OC) & 3) == 0 && (((size_t)row0 * p.OC) & 3) == 0) {
-                        for (int i = lane * 4; i + 3 < count; i += 128)
-                            *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
-                        for (int i = (count & ~3) + lane; i < count; i += 32) dst[i] = src[i];
-                    } else {
-                        for (int i = lane; i < count; i += 32) dst[i] = src[i];
+                if constexpr (STAGE_OUT) {
+                    // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
+                    __syncwarp();
+                    const int row0 = m_tile * kBM + quarter * 32;
+                    const int rows = min(32, p.M_total - row0);
+                    if (rows > 0) {
+                        const int count = rows * p.OC;
+                        const float *src = s_out + (size_t)quarter * 32 * p.OC;
+                        float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
+                        if ((((size_t)quarter * 32 * p.OC) & 3) == 0 && (((size_t)row0 * p.OC) & 3) == 0) {
+                            for (int i = lane * 4; i + 3 < count; i += 128)
+                                *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
+                            for (int i = (count & ~3) + lane; i < count; i += 32) dst[i] = src[i];
+                        } else {
+                            for (int i = lane; i < count; i += 32) dst[i] = src[i];
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
             }   // mi
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
