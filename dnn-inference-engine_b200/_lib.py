@@ -64,6 +64,13 @@ _sig("dnnb_net_profile_read", c_void_p, FP, IP)
 _sig("dnnb_net_destroy", c_void_p)
 _sig("dnnb_host_alloc", c_size_t, ctypes.POINTER(c_void_p))
 _sig("dnnb_host_free", c_void_p)
+_sig("dnnb_postprocess", c_int, c_void_p, c_int, c_float, ctypes.c_double, c_int, c_void_p, c_void_p)
+_sig("dnnb_postprocess_candidates", c_int, c_void_p, c_int, c_void_p)
+_sig("dnnb_nms", c_int, c_void_p, c_int, c_float, ctypes.c_double, c_int, c_void_p, c_void_p)
+_sig("dnnb_net_set_detect", c_void_p, c_float, ctypes.c_double, c_int)
+_sig("dnnb_net_detect_async", c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_detect_u8_async", c_void_p, c_void_p, c_int, c_void_p, c_void_p)
+_sig("dnnb_net_detect_device", c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p)
 _sig("dnnb_measure_mma_peak", c_int, c_int, FP)
 _sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 
@@ -72,7 +79,14 @@ EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
            "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
-           "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained"]
+           "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
+           "dnnb_postprocess", "dnnb_postprocess_candidates", "dnnb_nms", "dnnb_net_set_detect",
+           "dnnb_net_detect_async", "dnnb_net_detect_u8_async", "dnnb_net_detect_device"]
+
+# struct dnnb_det { int cls, left, top, right, bottom; float score; }
+DET_DTYPE = np.dtype([("cls", np.int32), ("left", np.int32), ("top", np.int32), ("right", np.int32),
+                      ("bottom", np.int32), ("score", np.float32)])
+CANDIDATES = 845
 
 
 def check(status):
@@ -190,6 +204,36 @@ class Net:
     def forward_u8_async(self, frames, out, bgr=True):
         check(lib.dnnb_net_forward_u8_async(self._h, frames.ctypes.data, 1 if bgr else 0, out.ctypes.data))
 
+    def set_detect(self, score_threshold=0.3, iou_threshold=0.3, max_det=32):
+        check(lib.dnnb_net_set_detect(self._h, score_threshold, iou_threshold, max_det))
+        self.max_det = max_det
+
+    def detect_async(self, x, dets, counts, bgr=True):
+        """Forward + on-device box decoding.  x: float32 [B,H,W,C] or uint8 frames; dets: DET_DTYPE
+        [B, max_det]; counts: int32 [B] (ideally PinnedArray.array), kept alive until sync()."""
+        assert dets.dtype == DET_DTYPE and dets.shape == (self.in_shape[0], getattr(self, "max_det", 32))
+        assert counts.dtype == np.int32 and counts.shape == (self.in_shape[0],)
+        if x.dtype == np.uint8:
+            check(lib.dnnb_net_detect_u8_async(self._h, x.ctypes.data, 1 if bgr else 0, dets.ctypes.data, counts.ctypes.data))
+        else:
+            assert x.dtype == np.float32
+            check(lib.dnnb_net_detect_async(self._h, x.ctypes.data, dets.ctypes.data, counts.ctypes.data))
+
+    def detect(self, x, bgr=True):
+        """-> (dets [B, max_det] DET_DTYPE, counts [B]); only the first min(count, max_det) entries of a row are valid."""
+        x = np.ascontiguousarray(x)
+        if x.dtype != np.uint8:
+            x = f32c(x)
+        assert tuple(x.shape) == self.in_shape, (x.shape, self.in_shape)
+        dets = np.zeros((self.in_shape[0], getattr(self, "max_det", 32)), dtype=DET_DTYPE)
+        counts = np.zeros(self.in_shape[0], dtype=np.int32)
+        self.detect_async(x, dets, counts, bgr)
+        self.sync()
+        return dets, counts
+
+    def detect_device(self, in_ptr, dets_ptr, counts_ptr, is_u8=False, bgr=True, stream=None):
+        check(lib.dnnb_net_detect_device(self._h, in_ptr, 1 if is_u8 else 0, 1 if bgr else 0, dets_ptr, counts_ptr, stream))
+
     def forward_device(self, in_ptr, out_ptr=None, stream=None):
         check(lib.dnnb_net_forward_device(self._h, in_ptr, out_ptr, stream))
 
@@ -234,6 +278,34 @@ class Net:
         n = c_int(0)
         check(lib.dnnb_net_launches_per_forward(self._h, ctypes.byref(n)))
         return n.value
+
+
+def postprocess(pred, score_threshold=0.3, iou_threshold=0.3, max_det=32, device=0):
+    """Head tensors [B,13,13,125] (or one [13,13,125]) -> (dets [B, max_det] DET_DTYPE, counts [B]) on the GPU."""
+    pred = f32c(pred).reshape(-1, 13, 13, 125)
+    dets = np.zeros((pred.shape[0], max_det), dtype=DET_DTYPE)
+    counts = np.zeros(pred.shape[0], dtype=np.int32)
+    check(lib.dnnb_postprocess(device, pred.ctypes.data, pred.shape[0], score_threshold, iou_threshold, max_det,
+                               dets.ctypes.data, counts.ctypes.data))
+    return dets, counts
+
+
+def postprocess_candidates(pred, device=0):
+    """All 845 decoded candidates per image, (row, col, box) order, before the threshold."""
+    pred = f32c(pred).reshape(-1, 13, 13, 125)
+    cand = np.zeros((pred.shape[0], CANDIDATES), dtype=DET_DTYPE)
+    check(lib.dnnb_postprocess_candidates(device, pred.ctypes.data, pred.shape[0], cand.ctypes.data))
+    return cand
+
+
+def nms(cand, score_threshold=0.3, iou_threshold=0.3, max_det=32, device=0):
+    """Threshold + stable sort + greedy NMS alone, on candidates [B,845] DET_DTYPE."""
+    cand = np.ascontiguousarray(cand, dtype=DET_DTYPE).reshape(-1, CANDIDATES)
+    dets = np.zeros((cand.shape[0], max_det), dtype=DET_DTYPE)
+    counts = np.zeros(cand.shape[0], dtype=np.int32)
+    check(lib.dnnb_nms(device, cand.ctypes.data, cand.shape[0], score_threshold, iou_threshold, max_det,
+                       dets.ctypes.data, counts.ctypes.data))
+    return dets, counts
 
 
 def measure_mma_peak(precision="tf32", device=0, seconds=0.0):

@@ -21,6 +21,7 @@
 #include "conv_rowpair.cuh"
 #include "conv_umma.cuh"
 #include "ops_simt.cuh"
+#include "postproc.cuh"
 
 namespace {
 
@@ -323,6 +324,12 @@ struct dnnb_net {
     // uint8 frames (proj3/__init__.py:8-12 without the resize): staging + the /255 table
     uint8_t *d_u8[2] = {nullptr, nullptr};
     float *d_lut = nullptr;
+    // on-device detection decoding (postproc.cuh): label boxes + counts, double-buffered like the outputs
+    void *d_dets[2] = {nullptr, nullptr};
+    int *d_counts[2] = {nullptr, nullptr};
+    float score_thr = 0.3f;      // proj3/yolov2tiny.py:156
+    double iou_thr = 0.3;        // :164
+    int max_det = 32;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
     int flip = 0;
@@ -1067,37 +1074,6 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
     return forward_impl(net, dev_in, dev_out, st);
 }
 
-int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out) {
-    if (check_net(net, true)) return 1;
-    if (!host_in || !host_out) return fail("null host buffer");
-    DeviceGuard g(net->device);
-    const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
-    Block &l = net->blocks.back();
-    if (!net->d_outf[0]) {
-        net->d_outf[0] = static_cast<float *>(l.d_out);
-        CK(cudaMalloc(&net->d_outf[1], l.out_elems * 4));
-    }
-    const int k = net->flip;
-    net->flip ^= 1;
-    // H2D on its own stream, as soon as the forward that last read this input buffer is done
-    CK(cudaStreamWaitEvent(net->copy_in, net->in_free[k], 0));
-    CK(cudaMemcpyAsync(net->d_in2[k], host_in, n_in * 4, cudaMemcpyHostToDevice, net->copy_in));
-    CK(cudaEventRecord(net->in_ready[k], net->copy_in));
-    // kernels: need the input, and the output buffer's previous D2H must have drained
-    CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
-    CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
-    if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
-    CK(cudaEventRecord(net->in_free[k], net->stream));
-    CK(cudaEventRecord(net->out_ready[k], net->stream));
-    // D2H on a third stream
-    CK(cudaStreamWaitEvent(net->copy_out, net->out_ready[k], 0));
-    CK(cudaMemcpyAsync(host_out, net->d_outf[k], l.out_elems * 4, cudaMemcpyDeviceToHost, net->copy_out));
-    CK(cudaEventRecord(net->out_free[k], net->copy_out));
-    net->last_final = net->d_outf[k];
-    net->last_in = net->d_in2[k];
-    return 0;
-}
-
 namespace {
 int ensure_u8(dnnb_net *net) {
     if (net->C != 3) return fail("uint8 frames need a 3-channel network input");
@@ -1133,12 +1109,55 @@ int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void 
     return forward_impl(net, net->d_in2[0], dev_out, st);
 }
 
-int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, float *host_out) {
+namespace {
+// One pipelined host-side forward: H2D on copy_in, kernels on net->stream, D2H on copy_out, with
+// double-buffered device input / output so that the copies of forwards i-1 and i+1 overlap the
+// kernels of forward i.  The result that travels back is either the head tensor (host_out) or,
+// with dets/counts, only the label boxes the on-device post-processing leaves.
+struct HostJob {
+    const void *host_in = nullptr;
+    bool u8 = false;
+    int bgr = 0;
+    float *host_out = nullptr;
+    dnnb_det *dets = nullptr;
+    int *counts = nullptr;
+};
+
+int ensure_detect(dnnb_net *net) {
+    const Block &l = net->blocks.back();
+    if (l.oh != postproc::kGrid || l.ow != postproc::kGrid || l.oc != postproc::kBoxes * postproc::kFields)
+        return fail("detection decoding needs a [B,13,13,125] network output, this one is [B,%d,%d,%d]", l.oh, l.ow, l.oc);
+    if (!net->d_dets[0]) {
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc(&net->d_dets[k], (size_t)net->B * net->max_det * sizeof(postproc::Det)));
+            CK(cudaMalloc(&net->d_counts[k], (size_t)net->B * sizeof(int)));
+        }
+    }
+    return 0;
+}
+
+cudaError_t launch_detect(dnnb_net *net, const float *pred, void *dets, void *counts, cudaStream_t st) {
+    postproc::Params q{};
+    q.pred = pred;
+    q.dets = static_cast<postproc::Det *>(dets);
+    q.counts = static_cast<int *>(counts);
+    q.B = net->B;
+    q.max_det = net->max_det;
+    q.score_thr = net->score_thr;
+    q.iou_thr = net->iou_thr;
+    const int grid = net->B < net->num_sms * 4 ? net->B : net->num_sms * 4;
+    postproc::detect_kernel<<<grid, postproc::kThreads, 0, st>>>(q);
+    return cudaGetLastError();
+}
+
+int enqueue_host_forward(dnnb_net *net, const HostJob &job) {
     if (check_net(net, true)) return 1;
-    if (!host_u8 || !host_out) return fail("null host buffer");
+    const bool detect = job.dets != nullptr;
+    if (!job.host_in || (!detect && !job.host_out) || (detect && !job.counts)) return fail("null host buffer");
     DeviceGuard g(net->device);
-    if (ensure_u8(net)) return 1;
-    const size_t n_in = (size_t)net->B * net->H * net->W * 3;
+    if (job.u8 && ensure_u8(net)) return 1;
+    if (detect && ensure_detect(net)) return 1;
+    const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
     Block &l = net->blocks.back();
     if (!net->d_outf[0]) {
         net->d_outf[0] = static_cast<float *>(l.d_out);
@@ -1146,20 +1165,96 @@ int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int b
     }
     const int k = net->flip;
     net->flip ^= 1;
+    // H2D on its own stream, as soon as the forward that last read this input buffer is done
     CK(cudaStreamWaitEvent(net->copy_in, net->in_free[k], 0));
-    CK(cudaMemcpyAsync(net->d_u8[k], host_u8, n_in, cudaMemcpyHostToDevice, net->copy_in));
+    if (job.u8) CK(cudaMemcpyAsync(net->d_u8[k], job.host_in, n_in, cudaMemcpyHostToDevice, net->copy_in));
+    else CK(cudaMemcpyAsync(net->d_in2[k], job.host_in, n_in * 4, cudaMemcpyHostToDevice, net->copy_in));
     CK(cudaEventRecord(net->in_ready[k], net->copy_in));
+    // kernels: need the input, and the output buffer's previous D2H must have drained
     CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
     CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
-    CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], bgr ? 1 : 0, net->stream));
+    if (job.u8) CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], job.bgr ? 1 : 0, net->stream));
     if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
+    if (detect) CK(launch_detect(net, net->d_outf[k], net->d_dets[k], net->d_counts[k], net->stream));
     CK(cudaEventRecord(net->in_free[k], net->stream));
     CK(cudaEventRecord(net->out_ready[k], net->stream));
+    // D2H on a third stream
     CK(cudaStreamWaitEvent(net->copy_out, net->out_ready[k], 0));
-    CK(cudaMemcpyAsync(host_out, net->d_outf[k], l.out_elems * 4, cudaMemcpyDeviceToHost, net->copy_out));
+    if (detect) {
+        CK(cudaMemcpyAsync(job.dets, net->d_dets[k], (size_t)net->B * net->max_det * sizeof(postproc::Det),
+                           cudaMemcpyDeviceToHost, net->copy_out));
+        CK(cudaMemcpyAsync(job.counts, net->d_counts[k], (size_t)net->B * sizeof(int), cudaMemcpyDeviceToHost, net->copy_out));
+    } else {
+        CK(cudaMemcpyAsync(job.host_out, net->d_outf[k], l.out_elems * 4, cudaMemcpyDeviceToHost, net->copy_out));
+    }
     CK(cudaEventRecord(net->out_free[k], net->copy_out));
     net->last_final = net->d_outf[k];
     net->last_in = net->d_in2[k];
+    return 0;
+}
+}  // namespace
+
+int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out) {
+    HostJob job;
+    job.host_in = host_in;
+    job.host_out = host_out;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, float *host_out) {
+    HostJob job;
+    job.host_in = host_u8;
+    job.u8 = true;
+    job.bgr = bgr;
+    job.host_out = host_out;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_set_detect(dnnb_net *net, float score_threshold, double iou_threshold, int max_det) {
+    if (check_net(net, false)) return 1;
+    if (max_det < 1 || max_det > postproc::kCand) return fail("max_det must be in [1, %d]", postproc::kCand);
+    if (net->d_dets[0] && max_det != net->max_det) return fail("max_det cannot change after the first detect call");
+    net->score_thr = score_threshold;
+    net->iou_thr = iou_threshold;
+    net->max_det = max_det;
+    return 0;
+}
+
+int dnnb_net_detect_async(dnnb_net *net, const float *host_in, dnnb_det *dets, int *counts) {
+    HostJob job;
+    job.host_in = host_in;
+    job.dets = dets;
+    job.counts = counts;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_detect_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, dnnb_det *dets, int *counts) {
+    HostJob job;
+    job.host_in = host_u8;
+    job.u8 = true;
+    job.bgr = bgr;
+    job.dets = dets;
+    job.counts = counts;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr, void *dev_dets, void *dev_counts,
+                           void *stream) {
+    if (check_net(net, true)) return 1;
+    if (!dev_in || !dev_dets || !dev_counts) return fail("null device buffer");
+    DeviceGuard g(net->device);
+    if (ensure_detect(net)) return 1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
+    const void *in = dev_in;
+    if (is_u8) {
+        if (ensure_u8(net)) return 1;
+        CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_in), net->d_in2[0], bgr ? 1 : 0, st));
+        in = net->d_in2[0];
+    }
+    net->last_final = static_cast<const float *>(net->blocks.back().d_out);
+    net->last_in = in;
+    if (forward_impl(net, in, nullptr, st)) return 1;
+    CK(launch_detect(net, net->last_final, dev_dets, dev_counts, st));
     return 0;
 }
 
@@ -1317,6 +1412,8 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->d_u8[1]) cudaFree(net->d_u8[1]);
     if (net->d_lut) cudaFree(net->d_lut);
     for (int k = 0; k < 2; ++k) {
+        if (net->d_dets[k]) cudaFree(net->d_dets[k]);
+        if (net->d_counts[k]) cudaFree(net->d_counts[k]);
         if (net->in_ready[k]) cudaEventDestroy(net->in_ready[k]);
         if (net->in_free[k]) cudaEventDestroy(net->in_free[k]);
         if (net->out_ready[k]) cudaEventDestroy(net->out_ready[k]);
@@ -1329,6 +1426,71 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->stream) cudaStreamDestroy(net->stream);
     delete net;
     return 0;
+}
+
+// ---------------------------------------------------------------------------- detection decoding
+// Stand-alone form of the on-device post-processing: host head tensors in, label boxes out.
+namespace {
+int postprocess_host(int device, const float *pred_host, const dnnb_det *cand_host, int batch, float score_thr,
+                     double iou_thr, int max_det, dnnb_det *cand_dump_host, dnnb_det *dets_host, int *counts_host) {
+    if (batch < 1) return fail("batch must be positive");
+    if (max_det < 1 || max_det > postproc::kCand) return fail("max_det must be in [1, %d]", postproc::kCand);
+    DeviceGuard g(device);
+    static_assert(sizeof(dnnb_det) == sizeof(postproc::Det), "dnnb_det layout");
+    const size_t n_pred = (size_t)batch * postproc::kCand * postproc::kFields;
+    const size_t n_cand = (size_t)batch * postproc::kCand;
+    DevBuf dpred, dcand, ddump, ddets, dcounts;
+    postproc::Params q{};
+    if (pred_host) {
+        if (dpred.alloc(n_pred * 4)) return 1;
+        CK(cudaMemcpy(dpred.p, pred_host, n_pred * 4, cudaMemcpyHostToDevice));
+        q.pred = dpred.f();
+    }
+    if (cand_host) {
+        if (dcand.alloc(n_cand * sizeof(dnnb_det))) return 1;
+        CK(cudaMemcpy(dcand.p, cand_host, n_cand * sizeof(dnnb_det), cudaMemcpyHostToDevice));
+        q.cand_in = static_cast<const postproc::Det *>(dcand.p);
+    }
+    if (cand_dump_host) {
+        if (ddump.alloc(n_cand * sizeof(dnnb_det))) return 1;
+        q.cand_out = static_cast<postproc::Det *>(ddump.p);
+    }
+    if (ddets.alloc((size_t)batch * max_det * sizeof(dnnb_det)) || dcounts.alloc((size_t)batch * sizeof(int))) return 1;
+    CK(cudaMemset(ddets.p, 0, (size_t)batch * max_det * sizeof(dnnb_det)));
+    q.dets = static_cast<postproc::Det *>(ddets.p);
+    q.counts = static_cast<int *>(dcounts.p);
+    q.B = batch;
+    q.max_det = max_det;
+    q.score_thr = score_thr;
+    q.iou_thr = iou_thr;
+    const int sms = sm_count();
+    postproc::detect_kernel<<<batch < sms * 4 ? batch : sms * 4, postproc::kThreads>>>(q);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    if (cand_dump_host) CK(cudaMemcpy(cand_dump_host, ddump.p, n_cand * sizeof(dnnb_det), cudaMemcpyDeviceToHost));
+    if (dets_host) CK(cudaMemcpy(dets_host, ddets.p, (size_t)batch * max_det * sizeof(dnnb_det), cudaMemcpyDeviceToHost));
+    if (counts_host) CK(cudaMemcpy(counts_host, dcounts.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+
+int dnnb_postprocess(int device, const float *pred_host, int batch, float score_threshold, double iou_threshold,
+                     int max_det, dnnb_det *dets_host, int *counts_host) {
+    if (!pred_host || !dets_host || !counts_host) return fail("dnnb_postprocess: null pointer");
+    return postprocess_host(device, pred_host, nullptr, batch, score_threshold, iou_threshold, max_det, nullptr,
+                            dets_host, counts_host);
+}
+
+int dnnb_postprocess_candidates(int device, const float *pred_host, int batch, dnnb_det *cand_host) {
+    if (!pred_host || !cand_host) return fail("dnnb_postprocess_candidates: null pointer");
+    return postprocess_host(device, pred_host, nullptr, batch, 0.3f, 0.3, 1, cand_host, nullptr, nullptr);
+}
+
+int dnnb_nms(int device, const dnnb_det *cand_host, int batch, float score_threshold, double iou_threshold, int max_det,
+             dnnb_det *dets_host, int *counts_host) {
+    if (!cand_host || !dets_host || !counts_host) return fail("dnnb_nms: null pointer");
+    return postprocess_host(device, nullptr, cand_host, batch, score_threshold, iou_threshold, max_det, nullptr,
+                            dets_host, counts_host);
 }
 
 // pinned host buffers for the end-to-end path (async H2D / D2H need page-locked memory)

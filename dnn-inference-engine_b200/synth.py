@@ -73,3 +73,20 @@ def build_yolov2tiny(builder, in_shape, weights, copy_variance=True):
                 nodes.append(cur)
     g.set_out_node(cur)
     return nodes
+
+
+def tame_head(weights, objectness_shift=-2.5):
+    """Random-init weights give head outputs of std ~4.5, i.e. boxes e^20 pixels wide on which
+    the reference's own `postprocessing` divides by zero.  For detection tests rescale the last
+    layer per field so that the head looks like a detector's: box offsets and sizes of order one,
+    objectness mostly low, class logits peaked -- a handful of confident boxes per image."""
+    field_scale = np.array([0.3, 0.3, 0.1, 0.1, 0.4] + [0.45] * 20, dtype=np.float32)
+    col_scale = np.tile(field_scale, 5)
+    out = [dict(w) for w in weights]
+    last = dict(out[-1])
+    last["kernel"] = (last["kernel"] * col_scale).astype(np.float32)
+    b = (last["biases"] * col_scale).astype(np.float32)
+    b[4::25] += objectness_shift
+    last["biases"] = b
+    out[-1] = last
+    return out

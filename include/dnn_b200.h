@@ -151,6 +151,44 @@ int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
 
 int dnnb_net_destroy(dnnb_net *net);
 
+/* ------------------------------------------------------------------------------------------
+ * 3. Detection decoding on the device: the step that follows the layer stack in the reference,
+ *    `postprocessing` (proj3/yolov2tiny.py:94-180) with its `iou` (:182-200),
+ *    `non_maximal_suppression` (:202-226), `sigmoid` (:228) and `softmax` (:231).  Input is the
+ *    [batch,13,13,125] head tensor; output per image: the label boxes that survive the score
+ *    threshold (reference 0.3, compared in float32) and the greedy class-agnostic NMS (IoU
+ *    threshold 0.3, compared in double), in the reference's order (score descending, stable).
+ *    Class names / colours are a host-side table lookup on `cls` (dnn_b200.py).  Box edges
+ *    saturate at +-2^29 (the reference has unbounded Python ints); a zero union, on which the
+ *    reference raises ZeroDivisionError, suppresses the box.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dnnb_det {
+    int cls;                      /* 0..19, Pascal VOC order of proj3/yolov2tiny.py:103 */
+    int left, top, right, bottom; /* int(center -/+ roi/2), pixels of the 416x416 input */
+    float score;                  /* sigmoid(tc) * max softmax */
+} dnnb_det;
+#define DNNB_CANDIDATES 845 /* 13 x 13 cells x 5 anchor boxes */
+
+/* dets_host [batch][max_det], counts_host [batch] = boxes kept (only min(count, max_det) stored) */
+int dnnb_postprocess(int device, const float *pred_host, int batch, float score_threshold,
+                     double iou_threshold, int max_det, dnnb_det *dets_host, int *counts_host);
+/* parity hooks: all 845 decoded candidates per image in (row, col, box) order, before the
+ * threshold; and the threshold + sort + NMS half alone on caller-supplied candidates */
+int dnnb_postprocess_candidates(int device, const float *pred_host, int batch, dnnb_det *cand_host);
+int dnnb_nms(int device, const dnnb_det *cand_host, int batch, float score_threshold,
+             double iou_threshold, int max_det, dnnb_det *dets_host, int *counts_host);
+
+/* Network form: forward + decoding enqueued together; only boxes and counts cross PCIe.
+ * Thresholds default to the reference's 0.3 / 0.3 and max_det to 32 per image.  The async forms
+ * pipeline like dnnb_net_forward_async (page-locked buffers, dnnb_net_sync). */
+int dnnb_net_set_detect(dnnb_net *net, float score_threshold, double iou_threshold, int max_det);
+int dnnb_net_detect_async(dnnb_net *net, const float *host_in, dnnb_det *dets_host, int *counts_host);
+int dnnb_net_detect_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, dnnb_det *dets_host,
+                             int *counts_host);
+/* input (fp32 NHWC, or uint8 frames with is_u8) and outputs all in device memory */
+int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr, void *dev_dets,
+                           void *dev_counts, void *stream);
+
 /* Page-locked host memory for the end-to-end path. */
 int dnnb_host_alloc(size_t bytes, void **out);
 int dnnb_host_free(void *p);

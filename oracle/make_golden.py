@@ -106,6 +106,37 @@ def small_ops(mod_ob, rng):
     return out
 
 
+def postproc_golden(ref_yolo):
+    """The reference's own `postprocessing` (proj3/yolov2tiny.py:94) on seeded head outputs."""
+    import postproc as pp
+    out = {}
+    stored = pp.synth_predictions(8, seed=11)                 # kept whole in the fixture
+    seeded = pp.synth_predictions(40, seed=12, spread=1.3)    # regenerated from the seed by the tests
+    out["pred_stored"] = stored
+    out["seeded_seed"], out["seeded_batch"], out["seeded_spread"] = 12, 40, 1.3
+    out["seeded_checksum"] = np.float64(seeded.astype(np.float64).sum())
+    rows, counts = [], []
+    for p in list(stored) + list(seeded):
+        boxes = ref_yolo.postprocessing(p)
+        counts.append(len(boxes))
+        for name, lt, rb, color in boxes:
+            rows.append([pp.CLASS_NAMES.index(name), lt[0], lt[1], rb[0], rb[1]])
+    out["det_count"] = np.array(counts, dtype=np.int64)
+    out["det_rows"] = np.array(rows, dtype=np.int64).reshape(-1, 5)
+    colors = np.zeros((pp.CLASSES, 3))
+    for c in range(pp.CLASSES):                               # one confident box of each class -> its colour
+        p = np.full((13, 13, 5, 25), -20, np.float32)
+        p[6, 6, 0, :5] = [0, 0, 0, 0, 10]
+        p[6, 6, 0, 5 + c] = 20
+        (name, lt, rb, color), = ref_yolo.postprocessing(p.reshape(13, 13, 125))
+        assert name == pp.CLASS_NAMES[c]
+        colors[c] = color
+        if c == 0:
+            out["single_box"] = np.array([lt[0], lt[1], rb[0], rb[1]], dtype=np.int64)
+    out["colors"] = colors
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")
@@ -116,6 +147,10 @@ def main():
     try:
         mod_ob, mod_avx = import_reference(work)
         np.savez_compressed(os.path.join(golden, "ops_small.npz"), **small_ops(mod_ob, np.random.default_rng(7)))
+        import yolov2tiny as ref_yolo      # imports dnn_openblas: needs the cwd set up above
+        pg = postproc_golden(ref_yolo)
+        np.savez_compressed(os.path.join(golden, "postproc.npz"), **pg)
+        print("postproc: %d images, %d boxes" % (len(pg["det_count"]), len(pg["det_rows"])))
         for wseed, iseed in [(0, 100), (1, 101)]:
             weights = make_weights(wseed)
             image = make_images(1, seed=iseed)
