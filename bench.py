@@ -336,7 +336,35 @@ def run_b200(args):
                                "h2d_bytes_per_step": int(args.global_batch * 416 * 416 * 3),
                                "note": "dnnb_net_forward_u8_async: uint8 BGR frames in, float32(u8/255.) + BGR->RGB "
                                        "(proj3/__init__.py:8-12 minus the resize) as one extra kernel on the device"}
-        hu8.free(); hout.free()
+        # frames in, label boxes out (SURVEY 8f1 + 8f3): the head tensor never leaves the device
+        max_det = 32
+        net.set_detect(max_det=max_det)
+        hdets = _lib.PinnedArray((n_mb, mb, max_det), dtype=_lib.DET_DTYPE)
+        hcnt = _lib.PinnedArray((n_mb, mb), dtype=np.int32)
+
+        def e2e_boxes_step():
+            for j in range(n_mb):
+                net.detect_async(u8[j], hdets.array[j], hcnt.array[j], True)
+            net.sync()
+
+        e2e_boxes_step()
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_boxes_step()
+        fence()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["uint8_frames_to_boxes"] = {
+            "value": args.global_batch * k_e2e / float(dt.item()), "unit": UNIT,
+            "h2d_bytes_per_step": int(args.global_batch * 416 * 416 * 3),
+            "d2h_bytes_per_step": int(args.global_batch * (max_det * _lib.DET_DTYPE.itemsize + 4)),
+            "boxes_per_image": float(np.minimum(hcnt.array, max_det).mean()),
+            "note": "dnnb_net_detect_u8_async: as uint8_frames, plus the reference's postprocessing (decode, 0.3 "
+                    "threshold, NMS; proj3/yolov2tiny.py:94-226) as one more kernel; only boxes cross PCIe. "
+                    "Random-init weights make far more candidates pass than a trained head would"}
+        hu8.free(); hout.free(); hdets.free(); hcnt.free()
 
     # ---- per-layer roofline (micro-batch, L2 flushed between repetitions)
     peaks = measured_peaks()

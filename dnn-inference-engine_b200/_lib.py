@@ -71,6 +71,9 @@ _sig("dnnb_net_set_detect", c_void_p, c_float, ctypes.c_double, c_int)
 _sig("dnnb_net_detect_async", c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("dnnb_net_detect_u8_async", c_void_p, c_void_p, c_int, c_void_p, c_void_p)
 _sig("dnnb_net_detect_device", c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p)
+_sig("dnnb_net_forward_frames_async", c_void_p, c_void_p, c_int, c_int, c_int, c_void_p)
+_sig("dnnb_net_detect_frames_async", c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p)
+_sig("dnnb_resize_input", c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p)
 _sig("dnnb_measure_mma_peak", c_int, c_int, FP)
 _sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 
@@ -81,7 +84,8 @@ EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
            "dnnb_postprocess", "dnnb_postprocess_candidates", "dnnb_nms", "dnnb_net_set_detect",
-           "dnnb_net_detect_async", "dnnb_net_detect_u8_async", "dnnb_net_detect_device"]
+           "dnnb_net_detect_async", "dnnb_net_detect_u8_async", "dnnb_net_detect_device",
+           "dnnb_net_forward_frames_async", "dnnb_net_detect_frames_async", "dnnb_resize_input"]
 
 # struct dnnb_det { int cls, left, top, right, bottom; float score; }
 DET_DTYPE = np.dtype([("cls", np.int32), ("left", np.int32), ("top", np.int32), ("right", np.int32),
@@ -201,6 +205,18 @@ class Net:
         self.sync()
         return out
 
+    def forward_frames(self, frames, bgr=True, out=None):
+        """frames: uint8 [B,h,w,3] of ANY h, w: cv2.resize to the network size, / 255., BGR -> RGB on
+        the device (all of proj3/__init__.py:8-12), then the network."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert frames.ndim == 4 and frames.shape[0] == self.in_shape[0] and frames.shape[3] == 3, frames.shape
+        if out is None:
+            out = np.empty(self.out_shape, dtype=np.float32)
+        check(lib.dnnb_net_forward_frames_async(self._h, frames.ctypes.data, frames.shape[1], frames.shape[2],
+                                                1 if bgr else 0, out.ctypes.data))
+        self.sync()
+        return out
+
     def forward_u8_async(self, frames, out, bgr=True):
         check(lib.dnnb_net_forward_u8_async(self._h, frames.ctypes.data, 1 if bgr else 0, out.ctypes.data))
 
@@ -214,7 +230,8 @@ class Net:
         assert dets.dtype == DET_DTYPE and dets.shape == (self.in_shape[0], getattr(self, "max_det", 32))
         assert counts.dtype == np.int32 and counts.shape == (self.in_shape[0],)
         if x.dtype == np.uint8:
-            check(lib.dnnb_net_detect_u8_async(self._h, x.ctypes.data, 1 if bgr else 0, dets.ctypes.data, counts.ctypes.data))
+            check(lib.dnnb_net_detect_frames_async(self._h, x.ctypes.data, x.shape[1], x.shape[2], 1 if bgr else 0,
+                                                   dets.ctypes.data, counts.ctypes.data))
         else:
             assert x.dtype == np.float32
             check(lib.dnnb_net_detect_async(self._h, x.ctypes.data, dets.ctypes.data, counts.ctypes.data))
@@ -224,7 +241,9 @@ class Net:
         x = np.ascontiguousarray(x)
         if x.dtype != np.uint8:
             x = f32c(x)
-        assert tuple(x.shape) == self.in_shape, (x.shape, self.in_shape)
+            assert tuple(x.shape) == self.in_shape, (x.shape, self.in_shape)
+        else:       # uint8 frames of any size are resized on the device
+            assert x.ndim == 4 and x.shape[0] == self.in_shape[0] and x.shape[3] == 3, x.shape
         dets = np.zeros((self.in_shape[0], getattr(self, "max_det", 32)), dtype=DET_DTYPE)
         counts = np.zeros(self.in_shape[0], dtype=np.int32)
         self.detect_async(x, dets, counts, bgr)
@@ -278,6 +297,18 @@ class Net:
         n = c_int(0)
         check(lib.dnnb_net_launches_per_forward(self._h, ctypes.byref(n)))
         return n.value
+
+
+def resize_input(frames, hw=416, bgr=True, device=0):
+    """proj3/__init__.py:8-12 on the GPU: uint8 [B,h,w,3] (or one [h,w,3]) -> float32 [B,hw,hw,3]."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    single = frames.ndim == 3
+    if single:
+        frames = frames[None]
+    out = np.empty((frames.shape[0], hw, hw, 3), dtype=np.float32)
+    check(lib.dnnb_resize_input(device, frames.ctypes.data, frames.shape[0], frames.shape[1], frames.shape[2], hw, hw,
+                                1 if bgr else 0, out.ctypes.data))
+    return out[0] if single else out
 
 
 def postprocess(pred, score_threshold=0.3, iou_threshold=0.3, max_det=32, device=0):

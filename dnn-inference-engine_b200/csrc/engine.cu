@@ -323,7 +323,11 @@ struct dnnb_net {
     const void *last_in = nullptr;           // fp32 device input of the most recent forward
     // uint8 frames (proj3/__init__.py:8-12 without the resize): staging + the /255 table
     uint8_t *d_u8[2] = {nullptr, nullptr};
+    size_t u8_capacity = 0;       // bytes per staging buffer
     float *d_lut = nullptr;
+    // cv2-exact bilinear resize of frames that are not in_h x in_w: per-axis offset / weight tables
+    int *d_resize_tab = nullptr;  // [xofs W][xw W][yofs H][yw H]
+    int resize_sh = 0, resize_sw = 0;
     // on-device detection decoding (postproc.cuh): label boxes + counts, double-buffered like the outputs
     void *d_dets[2] = {nullptr, nullptr};
     int *d_counts[2] = {nullptr, nullptr};
@@ -1075,21 +1079,76 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
 }
 
 namespace {
-int ensure_u8(dnnb_net *net) {
+cudaError_t dnnb_sync_streams(dnnb_net *net) {
+    cudaError_t e = cudaStreamSynchronize(net->stream);
+    if (e == cudaSuccess && net->copy_in) e = cudaStreamSynchronize(net->copy_in);
+    if (e == cudaSuccess && net->copy_out) e = cudaStreamSynchronize(net->copy_out);
+    return e;
+}
+
+// One axis of cv::resize's INTER_LINEAR set-up for 8-bit images (OpenCV resize.cpp), in its
+// arithmetic: double scale, float32 fractional position, weights short(round_half_even(w * 2048)).
+// `clamp_x`: the x-axis border rule (offset clamped, weight reset); rows are clipped at fetch time.
+void resize_axis_table(int src, int dst, bool clamp_x, int *ofs, int *wts) {
+    const double scale = 1.0 / ((double)dst / (double)src);
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (clamp_x) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= src - 1) { s = src - 1; f = 0.f; }
+        }
+        ofs[d] = s;
+        const int w0 = (int)lrintf((1.f - f) * 2048.f), w1 = (int)lrintf(f * 2048.f);
+        wts[d] = (w0 & 0xffff) | (w1 << 16);
+    }
+}
+
+int ensure_u8(dnnb_net *net, int src_h = 0, int src_w = 0) {
     if (net->C != 3) return fail("uint8 frames need a 3-channel network input");
-    const size_t n = (size_t)net->B * net->H * net->W * 3;
-    if (n % 12 != 0) return fail("uint8 frames: B*H*W must be a multiple of 4");
+    if (src_h <= 0) src_h = net->H;
+    if (src_w <= 0) src_w = net->W;
+    const size_t n = (size_t)net->B * src_h * src_w * 3;
+    if (src_h == net->H && src_w == net->W && n % 12 != 0) return fail("uint8 frames: B*H*W must be a multiple of 4");
     if (!net->d_lut) {
         float lut[256];
         for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);   // numpy: uint8 / 255. -> float64 -> float32
         CK(cudaMalloc(&net->d_lut, sizeof(lut)));
         CK(cudaMemcpy(net->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&net->d_u8[0], n));
-        CK(cudaMalloc(&net->d_u8[1], n));
+    }
+    if (n > net->u8_capacity) {
+        CK(dnnb_sync_streams(net));          // earlier forwards may still read the old staging buffers
+        for (int k = 0; k < 2; ++k) {
+            if (net->d_u8[k]) CK(cudaFree(net->d_u8[k]));
+            net->d_u8[k] = nullptr;
+            CK(cudaMalloc(&net->d_u8[k], n));
+        }
+        net->u8_capacity = n;
+    }
+    if ((src_h != net->H || src_w != net->W) && (src_h != net->resize_sh || src_w != net->resize_sw)) {
+        CK(dnnb_sync_streams(net));          // ... or the old tables
+        std::vector<int> tab(2 * (size_t)net->W + 2 * (size_t)net->H);
+        resize_axis_table(src_w, net->W, true, tab.data(), tab.data() + net->W);
+        resize_axis_table(src_h, net->H, false, tab.data() + 2 * net->W, tab.data() + 2 * net->W + net->H);
+        if (!net->d_resize_tab) CK(cudaMalloc(&net->d_resize_tab, tab.size() * sizeof(int)));
+        CK(cudaMemcpy(net->d_resize_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        net->resize_sh = src_h;
+        net->resize_sw = src_w;
     }
     return 0;
 }
-cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f32, int swap_rb, cudaStream_t st) {
+cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f32, int swap_rb, cudaStream_t st,
+                              int src_h = 0, int src_w = 0) {
+    if (src_h > 0 && src_w > 0 && (src_h != net->H || src_w != net->W)) {
+        simt::ResizeParams q{};
+        q.src = dev_u8; q.dst = dev_f32;
+        q.xofs = net->d_resize_tab; q.xw = q.xofs + net->W; q.yofs = q.xw + net->W; q.yw = q.yofs + net->H;
+        q.lut = net->d_lut;
+        q.B = net->B; q.SH = src_h; q.SW = src_w; q.DH = net->H; q.DW = net->W; q.swap_rb = swap_rb;
+        simt::resize_bilinear_u8_kernel<<<ew_grid((size_t)net->B * net->H * net->W, net->num_sms), 256, 0, st>>>(q);
+        return cudaGetLastError();
+    }
     const size_t groups = (size_t)net->B * net->H * net->W / 4;
     simt::preprocess_u8_kernel<<<ew_grid(groups, net->num_sms), 256, 0, st>>>(
         reinterpret_cast<const uint32_t *>(dev_u8), reinterpret_cast<float4 *>(dev_f32), groups, net->d_lut, swap_rb);
@@ -1118,6 +1177,7 @@ struct HostJob {
     const void *host_in = nullptr;
     bool u8 = false;
     int bgr = 0;
+    int src_h = 0, src_w = 0;     // uint8 frames of another size: resized on the device (0 = network size)
     float *host_out = nullptr;
     dnnb_det *dets = nullptr;
     int *counts = nullptr;
@@ -1155,9 +1215,11 @@ int enqueue_host_forward(dnnb_net *net, const HostJob &job) {
     const bool detect = job.dets != nullptr;
     if (!job.host_in || (!detect && !job.host_out) || (detect && !job.counts)) return fail("null host buffer");
     DeviceGuard g(net->device);
-    if (job.u8 && ensure_u8(net)) return 1;
+    if (job.u8 && (job.src_h < 0 || job.src_w < 0 || (job.src_h > 0) != (job.src_w > 0))) return fail("bad frame size");
+    if (job.u8 && ensure_u8(net, job.src_h, job.src_w)) return 1;
     if (detect && ensure_detect(net)) return 1;
-    const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
+    const size_t n_in = job.u8 ? (size_t)net->B * (job.src_h ? job.src_h : net->H) * (job.src_w ? job.src_w : net->W) * 3
+                               : (size_t)net->B * net->H * net->W * net->C;
     Block &l = net->blocks.back();
     if (!net->d_outf[0]) {
         net->d_outf[0] = static_cast<float *>(l.d_out);
@@ -1173,7 +1235,7 @@ int enqueue_host_forward(dnnb_net *net, const HostJob &job) {
     // kernels: need the input, and the output buffer's previous D2H must have drained
     CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
     CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
-    if (job.u8) CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], job.bgr ? 1 : 0, net->stream));
+    if (job.u8) CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], job.bgr ? 1 : 0, net->stream, job.src_h, job.src_w));
     if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
     if (detect) CK(launch_detect(net, net->d_outf[k], net->d_dets[k], net->d_counts[k], net->stream));
     CK(cudaEventRecord(net->in_free[k], net->stream));
@@ -1207,6 +1269,31 @@ int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int b
     job.u8 = true;
     job.bgr = bgr;
     job.host_out = host_out;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_forward_frames_async(dnnb_net *net, const unsigned char *host_frames, int src_h, int src_w, int bgr,
+                                  float *host_out) {
+    HostJob job;
+    job.host_in = host_frames;
+    job.u8 = true;
+    job.bgr = bgr;
+    job.src_h = src_h;
+    job.src_w = src_w;
+    job.host_out = host_out;
+    return enqueue_host_forward(net, job);
+}
+
+int dnnb_net_detect_frames_async(dnnb_net *net, const unsigned char *host_frames, int src_h, int src_w, int bgr,
+                                 dnnb_det *dets, int *counts) {
+    HostJob job;
+    job.host_in = host_frames;
+    job.u8 = true;
+    job.bgr = bgr;
+    job.src_h = src_h;
+    job.src_w = src_w;
+    job.dets = dets;
+    job.counts = counts;
     return enqueue_host_forward(net, job);
 }
 
@@ -1411,6 +1498,7 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->d_u8[0]) cudaFree(net->d_u8[0]);
     if (net->d_u8[1]) cudaFree(net->d_u8[1]);
     if (net->d_lut) cudaFree(net->d_lut);
+    if (net->d_resize_tab) cudaFree(net->d_resize_tab);
     for (int k = 0; k < 2; ++k) {
         if (net->d_dets[k]) cudaFree(net->d_dets[k]);
         if (net->d_counts[k]) cudaFree(net->d_counts[k]);
@@ -1425,6 +1513,34 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->d_flush) cudaFree(net->d_flush);
     if (net->stream) cudaStreamDestroy(net->stream);
     delete net;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- input preprocessing
+int dnnb_resize_input(int device, const unsigned char *frames_host, int batch, int src_h, int src_w, int dst_h,
+                      int dst_w, int bgr, float *out_host) {
+    if (!frames_host || !out_host) return fail("dnnb_resize_input: null pointer");
+    if (batch < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return fail("dnnb_resize_input: bad shape");
+    DeviceGuard g(device);
+    const size_t n_src = (size_t)batch * src_h * src_w * 3, n_dst = (size_t)batch * dst_h * dst_w * 3;
+    std::vector<int> tab(2 * (size_t)dst_w + 2 * (size_t)dst_h);
+    resize_axis_table(src_w, dst_w, true, tab.data(), tab.data() + dst_w);
+    resize_axis_table(src_h, dst_h, false, tab.data() + 2 * dst_w, tab.data() + 2 * dst_w + dst_h);
+    float lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);
+    DevBuf dsrc, ddst, dtab, dlut;
+    if (dsrc.alloc(n_src) || ddst.alloc(n_dst * 4) || dtab.alloc(tab.size() * 4) || dlut.alloc(sizeof(lut))) return 1;
+    CK(cudaMemcpy(dsrc.p, frames_host, n_src, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dtab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dlut.p, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    simt::ResizeParams q{};
+    q.src = static_cast<const uint8_t *>(dsrc.p); q.dst = ddst.f();
+    q.xofs = static_cast<const int *>(dtab.p); q.xw = q.xofs + dst_w; q.yofs = q.xw + dst_w; q.yw = q.yofs + dst_h;
+    q.lut = dlut.f();
+    q.B = batch; q.SH = src_h; q.SW = src_w; q.DH = dst_h; q.DW = dst_w; q.swap_rb = bgr ? 1 : 0;
+    simt::resize_bilinear_u8_kernel<<<ew_grid((size_t)batch * dst_h * dst_w, sm_count()), 256>>>(q);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_host, ddst.p, n_dst * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

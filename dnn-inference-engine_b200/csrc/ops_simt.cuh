@@ -320,6 +320,53 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint32_t *in, 
     }
 }
 
+// The whole of proj3/__init__.py:8-12 for frames of any size: cv2.resize's 8-bit INTER_LINEAR
+// (OpenCV resize.cpp: 11-bit fixed-point weights, horizontal pass in int32, vertical pass
+// ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2), then lut[v] = float32(v / 255.)
+// and the channel reversal.  The per-axis offset / weight tables are built on the host with
+// OpenCV's float32 arithmetic (engine.cu: resize_axis_table), so the result is bit-identical to
+// cv2 + numpy.  One thread = one output pixel (3 channels).
+struct ResizeParams {
+    const uint8_t *src;   // [B][SH][SW][3]
+    float *dst;           // [B][DH][DW][3]
+    const int *xofs;      // [DW] left source column (already clamped)
+    const int *xw;        // [DW] weights packed a0 | a1 << 16
+    const int *yofs;      // [DH] upper source row (NOT clamped: may be -1 or SH-1)
+    const int *yw;        // [DH] weights packed b0 | b1 << 16
+    const float *lut;     // [256]
+    int B, SH, SW, DH, DW, swap_rb;
+};
+__global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const ResizeParams p) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = p.lut[threadIdx.x];
+    __syncthreads();
+    const size_t total = (size_t)p.B * p.DH * p.DW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int dx = (int)(i % p.DW);
+        const size_t t = i / p.DW;
+        const int dy = (int)(t % p.DH);
+        const size_t n = t / p.DH;
+        const int x0 = __ldg(p.xofs + dx), x1 = min(x0 + 1, p.SW - 1);
+        const int xw = __ldg(p.xw + dx), a0 = xw & 0xffff, a1 = xw >> 16;
+        const int ys = __ldg(p.yofs + dy);
+        const int y0 = min(max(ys, 0), p.SH - 1), y1 = min(max(ys + 1, 0), p.SH - 1);
+        const int yw = __ldg(p.yw + dy), b0 = yw & 0xffff, b1 = yw >> 16;
+        const uint8_t *r0 = p.src + ((n * p.SH + y0) * p.SW) * 3;
+        const uint8_t *r1 = p.src + ((n * p.SH + y1) * p.SW) * 3;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int h0 = (int)__ldg(r0 + x0 * 3 + c) * a0 + (int)__ldg(r0 + x1 * 3 + c) * a1;
+            const int h1 = (int)__ldg(r1 + x0 * 3 + c) * a0 + (int)__ldg(r1 + x1 * 3 + c) * a1;
+            const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v[c] = lut[min(max(o, 0), 255)];
+        }
+        float *o = p.dst + i * 3;
+        if (p.swap_rb) { o[0] = v[2]; o[1] = v[1]; o[2] = v[0]; }
+        else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+    }
+}
+
 template <typename TIn>
 __global__ void cast_output_kernel(const TIn *in, float *out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -116,6 +116,16 @@ int dnnb_net_forward_async(dnnb_net *net, const float *host_in, float *host_out)
 int dnnb_net_forward_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, float *host_out);
 int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void *dev_out, void *stream);
 
+/* Frames of ANY size: the whole of proj3/__init__.py:8-12 (resize_input) on the device --
+ * cv2.resize(frame, (in_w, in_h)) [8-bit INTER_LINEAR, bit-identical to OpenCV's fixed-point
+ * path], / 255., BGR -> RGB, float32 -- as the one kernel in front of block 0.  host_frames is
+ * uint8 [batch][src_h][src_w][3].  dnnb_net_detect_frames_async (section 3) also decodes the boxes. */
+int dnnb_net_forward_frames_async(dnnb_net *net, const unsigned char *host_frames, int src_h, int src_w,
+                                  int bgr, float *host_out);
+/* op-level form, host in / host out: float32 [batch][dst_h][dst_w][3] */
+int dnnb_resize_input(int device, const unsigned char *frames_host, int batch, int src_h, int src_w,
+                      int dst_h, int dst_w, int bgr, float *out_host);
+
 /* Waits for everything queued on the network's own stream. */
 int dnnb_net_sync(dnnb_net *net);
 
@@ -185,6 +195,8 @@ int dnnb_net_set_detect(dnnb_net *net, float score_threshold, double iou_thresho
 int dnnb_net_detect_async(dnnb_net *net, const float *host_in, dnnb_det *dets_host, int *counts_host);
 int dnnb_net_detect_u8_async(dnnb_net *net, const unsigned char *host_u8, int bgr, dnnb_det *dets_host,
                              int *counts_host);
+int dnnb_net_detect_frames_async(dnnb_net *net, const unsigned char *host_frames, int src_h, int src_w,
+                                 int bgr, dnnb_det *dets_host, int *counts_host);
 /* input (fp32 NHWC, or uint8 frames with is_u8) and outputs all in device memory */
 int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr, void *dev_dets,
                            void *dev_counts, void *stream);

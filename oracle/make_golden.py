@@ -137,6 +137,26 @@ def postproc_golden(ref_yolo):
     return out
 
 
+def resize_golden():
+    """cv2.resize (what proj3/__init__.py:9 calls) on seeded frames; small target sizes keep the
+    fixture small, one 416x416 case is stored as a checksum and a strided sample."""
+    import cv2
+    rng = np.random.default_rng(21)
+    out = {"cv2_version": np.array(cv2.__version__)}
+    cases = [(50, 70, 96), (200, 150, 96), (96, 96, 96), (97, 33, 96), (48, 48, 96), (3, 5, 32), (1, 1, 32), (131, 207, 64)]
+    out["cases"] = np.array(cases, dtype=np.int64)
+    for i, (h, w, d) in enumerate(cases):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if i == 1:
+            img[:, :, :] = (np.arange(w)[None, :, None] * 255 // max(1, w - 1)).astype(np.uint8)    # a smooth ramp
+        out["src_%d" % i] = img
+        out["dst_%d" % i] = cv2.resize(img, (d, d))
+    big = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    r = cv2.resize(big, (416, 416))
+    out["big_src"], out["big_sum"], out["big_sample"] = big, np.int64(r.astype(np.int64).sum()), r[::13, ::7].copy()
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")
@@ -147,6 +167,7 @@ def main():
     try:
         mod_ob, mod_avx = import_reference(work)
         np.savez_compressed(os.path.join(golden, "ops_small.npz"), **small_ops(mod_ob, np.random.default_rng(7)))
+        np.savez_compressed(os.path.join(golden, "resize.npz"), **resize_golden())
         import yolov2tiny as ref_yolo      # imports dnn_openblas: needs the cwd set up above
         pg = postproc_golden(ref_yolo)
         np.savez_compressed(os.path.join(golden, "postproc.npz"), **pg)
