@@ -60,13 +60,22 @@ constexpr int kWBytes = 2 * kWOperandBytes;        // tap pairs (dj 0,1) and (dj
 constexpr int kRawDepth = 6;                       // raw-pixel staging ring: tiles whose global loads are in flight
 constexpr int kRawRowBytes = kPatchPx * 12;        // one patch row of raw 12-byte pixels (= kGroups * 48)
 constexpr int kRawBytes = (kPatchRows * kRawRowBytes + 127) / 128 * 128;
-constexpr int kSmemBytes = kStages * kPatchBytes + kRawDepth * kRawBytes + kWBytes + 1024 + 256;
+// uint8 frames (IN_U8): a raw patch row is 160 3-byte pixels [w0-16, w0+144) = 480 bytes, so that both
+// ends of every bulk copy fall on 16-byte boundaries (needs W % 16 == 0)
+constexpr int kRawPxU8 = 160;
+constexpr int kRawLeadU8 = 16;
+constexpr int kRawRowBytesU8 = kRawPxU8 * 3;
+static_assert(kPatchRows * kRawRowBytesU8 <= kRawBytes, "uint8 rows fit the raw slots");
+constexpr int kSmemBytes = kStages * kPatchBytes + kRawDepth * kRawBytes + kWBytes + 1024 + 256 + 1024 /*uint8 LUT*/;
 static_assert(kStages % kMmaWarps == 0 && kAccStages % kMmaWarps == 0 && kAccStages % kEpilogueGroups == 0,
               "one owner warp per ring slot");
 static_assert(kAccCols * kAccStages <= 512, "accumulators must fit TMEM");
 
 struct Params {
-    const float *in;     // [B, H, W, 3] fp32
+    const void *in;      // [B, H, W, 3] fp32, or uint8 frames (IN_U8)
+    const uint32_t *lut; // IN_U8: operand bit pattern of float32(v / 255.) for v = 0..255, already rounded
+                         // the way the fp32 path rounds (tf32: + half ulp; bf16: RN, in the low 16 bits)
+    int swap_rb;         // IN_U8: frames are BGR, the network wants RGB (proj3/__init__.py:11)
     void *out;           // [B, H/2, W/2, 16]
     const void *wpack;   // 2 stacked operands in canonical no-swizzle layout (see pack_weights)
     const float *scale;  // [16]
@@ -80,7 +89,7 @@ struct Params {
     float *prepool;      // debug: also dump the pre-pool activations [B,H,W,16] fp32
 };
 
-template <bool BF16, bool OUT_BF16>
+template <bool BF16, bool OUT_BF16, bool IN_U8 = false>
 __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_w + kWBytes + 512);
     float *s_scale = reinterpret_cast<float *>(s_w + kWBytes + 1024);
     float *s_shift = s_scale + 16;
+    uint32_t *s_lut = reinterpret_cast<uint32_t *>(s_w + kWBytes + 1024 + 256);
 
     const uint32_t bar_full = ptx::smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * kStages;
@@ -115,6 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     for (int i = threadIdx.x; i < kWBytes / 16; i += kThreads)
         reinterpret_cast<uint4 *>(s_w)[i] = reinterpret_cast<const uint4 *>(p.wpack)[i];
     if (threadIdx.x < 16) { s_scale[threadIdx.x] = p.scale[threadIdx.x]; s_shift[threadIdx.x] = p.shift[threadIdx.x]; }
+    if constexpr (IN_U8) {
+        if (threadIdx.x < 256) s_lut[threadIdx.x] = p.lut[threadIdx.x];
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weights were written by the generic proxy
     ptx::tc_fence_before();
     __syncthreads();
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         // ------------------------------------------------------------ patch producers
         // 340 groups of 4 pixels per patch; thread handles groups tid, tid + 256.  The group ->
         // (patch row, column group) split does not depend on the tile: hoist it.
-        int g_row[kRounds], g_dst[kRounds], g_px[kRounds];
+        int g_row[kRounds], g_dst[kRounds], g_px[kRounds], g_src[kRounds];
 #pragma unroll
         for (int it = 0; it < kRounds; ++it) {
             const int g = threadIdx.x + kProducerWarps * 32 * it;
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             g_row[it] = g < kTileGroups ? r : 1 << 20;              // invalid groups fail the row test below
             g_px[it] = 4 * gx - 4;
             g_dst[it] = r * kPatchRowBytes + gx * 64;
+            g_src[it] = IN_U8 ? r * kRawRowBytesU8 + (4 * gx - 4 + kRawLeadU8) * 3 : g * 48;
         }
         Coord tc = decode(tile_begin);
         for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
@@ -166,13 +180,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             for (int it = 0; it < kRounds; ++it) {
                 if (g_row[it] < kPatchRows) {
                     const bool ok = (unsigned)(row0 + g_row[it]) < (unsigned)p.H && (unsigned)(w0 + g_px[it]) < (unsigned)p.W;
+                    uint4 *dst = reinterpret_cast<uint4 *>(patch + g_dst[it]);
+                    if constexpr (IN_U8) {
+                        // 4 pixels = 12 bytes; the table holds the finished operand bits of float32(v / 255.)
+                        uint32_t w3[3] = {0u, 0u, 0u};
+                        if (ok) {
+                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + g_src[it]);
+                            w3[0] = src[0]; w3[1] = src[1]; w3[2] = src[2];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t v[3];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const int byte = 3 * q + c;
+                                v[c] = s_lut[(w3[byte >> 2] >> (8 * (byte & 3))) & 0xffu];
+                            }
+                            const uint32_t c0 = p.swap_rb ? v[2] : v[0], c2 = p.swap_rb ? v[0] : v[2];
+                            uint4 o;
+                            if constexpr (BF16) { o.x = c0 | (v[1] << 16); o.y = c2; o.z = 0u; o.w = 0u; }
+                            else { o.x = c0; o.y = v[1]; o.z = c2; o.w = 0u; }
+                            if (!ok) o = make_uint4(0u, 0u, 0u, 0u);      // outside the image: zeros (SAME padding)
+                            dst[q] = o;
+                        }
+                        continue;
+                    }
                     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a;      // outside the image: zeros (SAME padding)
                     if (ok) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(raw + (threadIdx.x + kProducerWarps * 32 * it) * 48);
+                        const uint4 *src = reinterpret_cast<const uint4 *>(raw + g_src[it]);
                         a = src[0]; b = src[1]; c = src[2];
                     }
                     const uint32_t f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-                    uint4 *dst = reinterpret_cast<uint4 *>(patch + g_dst[it]);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 o;
@@ -209,15 +247,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                 const int slot = t % kRawDepth;
                 ptx::mbar_wait(bar_rempty + 8 * slot, ((t / kRawDepth) & 1) ^ 1);
                 const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
-                const int px_lo = w0 - 4 > 0 ? w0 - 4 : 0;
-                const int px_hi = w0 + kPatchPx - 4 < p.W ? w0 + kPatchPx - 4 : p.W;
+                constexpr int lead = IN_U8 ? kRawLeadU8 : 4, span = IN_U8 ? kRawPxU8 : kPatchPx;
+                constexpr int px_bytes = IN_U8 ? 3 : 12, row_bytes = IN_U8 ? kRawRowBytesU8 : kRawRowBytes;
+                const int px_lo = w0 - lead > 0 ? w0 - lead : 0;
+                const int px_hi = w0 + span - lead < p.W ? w0 + span - lead : p.W;
                 const int r_lo = row0 < 0 ? -row0 : 0;
                 const int r_hi = row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0;
-                const uint32_t bytes = (uint32_t)(px_hi - px_lo) * 12u;       // multiple of 48: pixels come in fours
+                const uint32_t bytes = (uint32_t)(px_hi - px_lo) * px_bytes;  // a multiple of 16 (pixels in fours / sixteens)
                 ptx::mbar_expect_tx(bar_rfull + 8 * slot, bytes * (uint32_t)(r_hi - r_lo));
-                const float *src = p.in + (((size_t)tc.n * p.H + (row0 + r_lo)) * p.W + px_lo) * 3;
-                uint32_t dst = raw_base + slot * kRawBytes + r_lo * kRawRowBytes + (px_lo - (w0 - 4)) * 12;
-                for (int r = r_lo; r < r_hi; ++r, src += (size_t)p.W * 3, dst += kRawRowBytes)
+                const uint8_t *src = static_cast<const uint8_t *>(p.in) +
+                                     (((size_t)tc.n * p.H + (row0 + r_lo)) * p.W + px_lo) * px_bytes;
+                uint32_t dst = raw_base + slot * kRawBytes + r_lo * row_bytes + (px_lo - (w0 - lead)) * px_bytes;
+                for (int r = r_lo; r < r_hi; ++r, src += (size_t)p.W * px_bytes, dst += row_bytes)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_rfull + 8 * slot) : "memory");
             }

@@ -325,6 +325,9 @@ struct dnnb_net {
     uint8_t *d_u8[2] = {nullptr, nullptr};
     size_t u8_capacity = 0;       // bytes per staging buffer
     float *d_lut = nullptr;
+    uint32_t *d_lut_conv0 = nullptr;   // the same table as finished block-0 operand bits (conv0_umma.cuh IN_U8)
+    bool cur_in_u8 = false;            // set by forward_impl for the block-0 launch
+    int cur_swap_rb = 0;
     // cv2-exact bilinear resize of frames that are not in_h x in_w: per-axis offset / weight tables
     int *d_resize_tab = nullptr;  // [xofs W][xw W][yofs H][yw H]
     int resize_sh = 0, resize_sw = 0;
@@ -583,9 +586,9 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     b.pool_separate = b.pool_k > 0 && !b.pool_fused;
 }
 
-template <bool BF16, bool OUT_BF16>
+template <bool BF16, bool OUT_BF16, bool IN_U8 = false>
 cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
-    auto kern = conv0::conv0_kernel<BF16, OUT_BF16>;
+    auto kern = conv0::conv0_kernel<BF16, OUT_BF16, IN_U8>;
     const int smem = conv0::kSmemBytes + 128;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, smem, done);
@@ -593,7 +596,11 @@ cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
     kern<<<grid, conv0::kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launch_conv0(const conv0::Params &p, bool bf16, bool out_bf16, int grid, cudaStream_t st) {
+cudaError_t launch_conv0(const conv0::Params &p, bool bf16, bool out_bf16, int grid, cudaStream_t st, bool in_u8 = false) {
+    if (in_u8) {
+        if (bf16) return out_bf16 ? launch_conv0_t<true, true, true>(p, grid, st) : launch_conv0_t<true, false, true>(p, grid, st);
+        return out_bf16 ? launch_conv0_t<false, true, true>(p, grid, st) : launch_conv0_t<false, false, true>(p, grid, st);
+    }
     if (bf16) return out_bf16 ? launch_conv0_t<true, true>(p, grid, st) : launch_conv0_t<true, false>(p, grid, st);
     return out_bf16 ? launch_conv0_t<false, true>(p, grid, st) : launch_conv0_t<false, false>(p, grid, st);
 }
@@ -653,9 +660,11 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         CK(run_simt_conv(p, b.in_bf16, b.out_bf16, st));
     } else if (b.family == DNNB_KERNEL_UMMA_CONV0) {
         conv0::Params p = b.c0;
-        p.in = static_cast<const float *>(in); p.out = conv_out; p.wpack = b.d_wpack;
+        p.in = in; p.out = conv_out; p.wpack = b.d_wpack;
         p.scale = b.d_scale; p.shift = b.d_shift; p.prepool = prepool;
-        CK(launch_conv0(p, b.op_bf16, b.out_bf16, b.grid, st));
+        const bool u8 = net->cur_in_u8 && &b == &net->blocks.front();
+        if (u8) { p.lut = net->d_lut_conv0; p.swap_rb = net->cur_swap_rb; }
+        CK(launch_conv0(p, b.op_bf16, b.out_bf16, b.grid, st, u8));
     } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
         if (b.map_a_base != in) {
             if (encode_map_a(net, b, in)) return 1;
@@ -688,9 +697,13 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
     return 0;
 }
 
-int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st) {
+// in_u8: dev_in holds uint8 frames of the network's size and block 0 is the conv0 kernel, which then
+// normalises them in its own loader (no separate preprocessing kernel, 3 instead of 12 bytes per pixel read)
+int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st, bool in_u8 = false, int swap_rb = 0) {
     const void *cur = dev_in;
     Block &first = net->blocks.front();
+    net->cur_in_u8 = in_u8;
+    net->cur_swap_rb = swap_rb;
     if (first.family != DNNB_KERNEL_SIMT && first.family != DNNB_KERNEL_UMMA_CONV0) {
         // a tcgen05 first block reads its storage type: TF32-rounded fp32, or bf16
         const size_t n = (size_t)net->B * net->H * net->W * net->C;
@@ -1116,6 +1129,16 @@ int ensure_u8(dnnb_net *net, int src_h = 0, int src_w = 0) {
         for (int i = 0; i < 256; ++i) lut[i] = (float)((double)i / 255.0);   // numpy: uint8 / 255. -> float64 -> float32
         CK(cudaMalloc(&net->d_lut, sizeof(lut)));
         CK(cudaMemcpy(net->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+        // block 0's operand bits for the same values: what cast + rounding in the fp32 path produce
+        uint32_t bits[256];
+        const bool bf16 = net->blocks.front().op_bf16;
+        for (int i = 0; i < 256; ++i) {
+            uint32_t u;
+            memcpy(&u, &lut[i], 4);
+            bits[i] = bf16 ? (uint32_t)host_bf16(lut[i]) : u + 0x1000u;
+        }
+        CK(cudaMalloc(&net->d_lut_conv0, sizeof(bits)));
+        CK(cudaMemcpy(net->d_lut_conv0, bits, sizeof(bits), cudaMemcpyHostToDevice));
     }
     if (n > net->u8_capacity) {
         CK(dnnb_sync_streams(net));          // earlier forwards may still read the old staging buffers
@@ -1138,6 +1161,13 @@ int ensure_u8(dnnb_net *net, int src_h = 0, int src_w = 0) {
     }
     return 0;
 }
+// uint8 frames of the network's own size go straight into the conv0 kernel when it is block 0
+bool u8_fused(const dnnb_net *net, int src_h, int src_w) {
+    static const bool off = getenv("DNNB_NO_U8_FUSION") != nullptr;
+    const bool same = (src_h <= 0 || src_h == net->H) && (src_w <= 0 || src_w == net->W);
+    return !off && same && net->blocks.front().family == DNNB_KERNEL_UMMA_CONV0 && net->W % 16 == 0;
+}
+
 cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f32, int swap_rb, cudaStream_t st,
                               int src_h = 0, int src_w = 0) {
     if (src_h > 0 && src_w > 0 && (src_h != net->H || src_w != net->W)) {
@@ -1162,10 +1192,11 @@ int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void 
     DeviceGuard g(net->device);
     if (ensure_u8(net)) return 1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
-    CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_u8), net->d_in2[0], bgr ? 1 : 0, st));
+    const bool fused = u8_fused(net, 0, 0);
+    if (!fused) CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_u8), net->d_in2[0], bgr ? 1 : 0, st));
     net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
-    net->last_in = net->d_in2[0];
-    return forward_impl(net, net->d_in2[0], dev_out, st);
+    net->last_in = fused ? nullptr : net->d_in2[0];
+    return fused ? forward_impl(net, dev_u8, dev_out, st, true, bgr ? 1 : 0) : forward_impl(net, net->d_in2[0], dev_out, st);
 }
 
 namespace {
@@ -1235,8 +1266,11 @@ int enqueue_host_forward(dnnb_net *net, const HostJob &job) {
     // kernels: need the input, and the output buffer's previous D2H must have drained
     CK(cudaStreamWaitEvent(net->stream, net->in_ready[k], 0));
     CK(cudaStreamWaitEvent(net->stream, net->out_free[k], 0));
-    if (job.u8) CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], job.bgr ? 1 : 0, net->stream, job.src_h, job.src_w));
-    if (forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream)) return 1;
+    const bool fused = job.u8 && u8_fused(net, job.src_h, job.src_w);
+    if (job.u8 && !fused) CK(launch_preprocess(net, net->d_u8[k], net->d_in2[k], job.bgr ? 1 : 0, net->stream, job.src_h, job.src_w));
+    if (fused ? forward_impl(net, net->d_u8[k], net->d_outf[k], net->stream, true, job.bgr ? 1 : 0)
+              : forward_impl(net, net->d_in2[k], net->d_outf[k], net->stream))
+        return 1;
     if (detect) CK(launch_detect(net, net->d_outf[k], net->d_dets[k], net->d_counts[k], net->stream));
     CK(cudaEventRecord(net->in_free[k], net->stream));
     CK(cudaEventRecord(net->out_ready[k], net->stream));
@@ -1251,7 +1285,7 @@ int enqueue_host_forward(dnnb_net *net, const HostJob &job) {
     }
     CK(cudaEventRecord(net->out_free[k], net->copy_out));
     net->last_final = net->d_outf[k];
-    net->last_in = net->d_in2[k];
+    net->last_in = fused ? nullptr : net->d_in2[k];
     return 0;
 }
 }  // namespace
@@ -1333,14 +1367,18 @@ int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr
     if (ensure_detect(net)) return 1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
     const void *in = dev_in;
+    bool fused = false;
     if (is_u8) {
         if (ensure_u8(net)) return 1;
-        CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_in), net->d_in2[0], bgr ? 1 : 0, st));
-        in = net->d_in2[0];
+        fused = u8_fused(net, 0, 0);
+        if (!fused) {
+            CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_in), net->d_in2[0], bgr ? 1 : 0, st));
+            in = net->d_in2[0];
+        }
     }
     net->last_final = static_cast<const float *>(net->blocks.back().d_out);
-    net->last_in = in;
-    if (forward_impl(net, in, nullptr, st)) return 1;
+    net->last_in = fused ? nullptr : in;
+    if (forward_impl(net, in, nullptr, st, fused, bgr ? 1 : 0)) return 1;
     CK(launch_detect(net, net->last_final, dev_dets, dev_counts, st));
     return 0;
 }
@@ -1499,6 +1537,7 @@ int dnnb_net_destroy(dnnb_net *net) {
     if (net->d_u8[1]) cudaFree(net->d_u8[1]);
     if (net->d_lut) cudaFree(net->d_lut);
     if (net->d_resize_tab) cudaFree(net->d_resize_tab);
+    if (net->d_lut_conv0) cudaFree(net->d_lut_conv0);
     for (int k = 0; k < 2; ++k) {
         if (net->d_dets[k]) cudaFree(net->d_dets[k]);
         if (net->d_counts[k]) cudaFree(net->d_counts[k]);

@@ -109,7 +109,11 @@ __device__ __forceinline__ bool iou_exceeds(const Det &a, const Det &b, double t
     const long long area_a = ((long long)a.right - a.left + 1) * ((long long)a.bottom - a.top + 1);
     const long long area_b = ((long long)b.right - b.left + 1) * ((long long)b.bottom - b.top + 1);
     const long long uni = area_a + area_b - inter;
+    // a float quotient settles every case that is not within 1e-3 of the threshold; the rest (and NaN)
+    // take the reference's arithmetic: int -> double conversions and one double division.
     // uni == 0 raises ZeroDivisionError in the reference; here IEEE division makes it +-inf / NaN
+    const float q = __fdividef((float)inter, (float)uni), tf = (float)thr;
+    if (fabsf(q - tf) > 1e-3f * (fabsf(tf) + 1.0f) && fabsf(q) < 1e30f) return q > tf;
     return __ddiv_rn((double)inter, (double)uni) > thr;
 }
 
@@ -179,8 +183,12 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(const Params p) {
             for (int t = 0; t < n; ++t) {
                 const Det cur = s_cand[s_sorted[t]];
                 bool drop = false;
-                for (int k = lane; k < nk; k += 32) drop |= iou_exceeds(cur, s_cand[s_kept[k]], p.iou_thr);
-                if (!__any_sync(0xffffffffu, drop)) {
+                for (int k0 = 0; k0 < nk && !drop; k0 += 32) {       // any overlap decides: stop at the first chunk that has one
+                    const int k = k0 + lane;
+                    const bool hit = k < nk && iou_exceeds(cur, s_cand[s_kept[k]], p.iou_thr);
+                    drop = __any_sync(0xffffffffu, hit);
+                }
+                if (!drop) {
                     if (lane == 0) {
                         s_kept[nk] = s_sorted[t];
                         if (nk < p.max_det) p.dets[(size_t)img * p.max_det + nk] = cur;
