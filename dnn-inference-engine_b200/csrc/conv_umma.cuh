@@ -43,6 +43,8 @@ struct Params {
     // tiled mode: tile = nb images x th rows x tw cols (all powers of two, product 128)
     int tw, th, nb, log2_tw, log2_th, tiles_w, tiles_h;
     int M_total;          // im2col mode: B*H*W
+    int m_base;           // im2col mode: first output pixel of this launch (a block may be cut into a main launch
+                          // of whole waves and a finer-tiled tail launch over the remaining rows)
     const float *scale;   // [num_n_tiles*BN]  gamma / sqrt(var + eps)      (1 when no BN)
     const float *shift;   // [num_n_tiles*BN]  (bias - mean) * scale         (bias when no BN)
     void *out;            // [B, OH, OW, OC]
@@ -167,7 +169,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if constexpr (IM2COL) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        const int m0 = (m_tile * MT + i) * kBM;
+                        const int m0 = p.m_base + (m_tile * MT + i) * kBM;
                         n0[i] = m0 / (p.H * p.W);
                         const int rem = m0 - n0[i] * (p.H * p.W);
                         h0[i] = rem / p.W;
@@ -350,7 +352,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
                 size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
                 if constexpr (IM2COL) {
-                    const int m = (m_tile * MT + mi) * kBM + row;
+                    const int m = p.m_base + (m_tile * MT + mi) * kBM + row;
                     valid = m < p.M_total;
                     out_pix = (size_t)m;
                 } else {
@@ -490,7 +492,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if constexpr (STAGE_OUT) {
                     // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
                     __syncwarp();
-                    const int row0 = m_tile * kBM + quarter * 32;
+                    const int row0 = p.m_base + m_tile * kBM + quarter * 32;
                     const int rows = min(32, p.M_total - row0);
                     if (rows > 0) {
                         const int count = rows * p.OC;

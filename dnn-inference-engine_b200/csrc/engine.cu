@@ -293,6 +293,12 @@ struct Block {
     rowpair::Params rp{};
     umma_conv::Params up{};
     CUtensorMap map_a{}, map_b{};
+    // tail launch (im2col blocks whose tile count is not a whole number of waves): the rows left after
+    // the last full wave, in finer tiles (smaller BN, MT = 1) so that they spread over all SMs
+    const UmmaEntry *umma_tail = nullptr;
+    CUtensorMap map_b_tail{};
+    umma_conv::Params up_tail{};
+    int grid_tail = 0;
     const void *map_a_base = nullptr;           // input pointer the A map was encoded for
     int bn = 0, swz = 0, grid = 0;
     // device memory
@@ -392,7 +398,9 @@ int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
     return 0;
 }
 
-int encode_map_b(Block &b) {
+int encode_map_b(Block &b, CUtensorMap *map = nullptr, int bn_rows = 0) {
+    if (!map) map = &b.map_b;
+    if (!bn_rows) bn_rows = b.bn;
     const int es = b.in_bf16 ? 2 : 4;
     const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
@@ -412,9 +420,9 @@ int encode_map_b(Block &b) {
     const int bkc = b.swz / es;
     cuuint64_t dims[4] = {(cuuint64_t)bkc, (cuuint64_t)ocp, (cuuint64_t)(b.ic / bkc), (cuuint64_t)(b.kh * b.kw)};
     cuuint64_t strides[3] = {(cuuint64_t)b.swz, (cuuint64_t)ocp * b.swz, (cuuint64_t)(b.ic / bkc) * ocp * b.swz};
-    cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)b.bn, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)bn_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_tiled(&b.map_b, dt, 4, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = g_encode_tiled(map, dt, 4, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("tensor-map encode (weights) failed: CUresult %d", (int)r);
@@ -533,9 +541,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 const long tiles2 = (m_rows + 255) / 256 * (ocp / bn);
                 // measured on B200 (TF32, batch 512): it pays when both accumulator stages survive
                 // (BN <= 128: block 3, 0.43 -> 0.28 ms) or when K is long enough to hide the serialised
-                // epilogue (block 7, K = 9216: 2.09 -> 1.98 ms); a wash or a loss otherwise (blocks 4-6)
+                // epilogue (block 7, K = 9216: 2.09 -> 1.98 ms; block 6, K = 4608, together with the tail
+                // launch below: 1.03 -> 1.00 ms and +1.4 % on the whole power-capped step, because a third
+                // less L2->SMEM traffic is also less energy); a loss for blocks 4-5
                 const long k_total = (long)b.kh * b.kw * b.ic;
-                bool want = tiles2 >= 2L * net->num_sms && (2 * bn <= 256 || k_total >= 8192);
+                bool want = tiles2 >= 2L * net->num_sms && (2 * bn <= 256 || k_total >= 4096);
                 if (getenv("DNNB_MT2_MASK")) want = (atoi(getenv("DNNB_MT2_MASK")) >> i) & 1;
                 UmmaKey key2 = key;
                 key2.mt = 2;
@@ -578,6 +588,40 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 }
                 const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;
+                // Wave quantisation: 1352 tiles on 148 SMs are 9.14 waves and cost 10.  Cut the block into a
+                // main launch of whole waves and a tail launch over the remaining rows with tiles small
+                // enough to occupy every SM once.  Every output element still sums its K blocks in the same
+                // order, so results do not change (tests: batch invariance, 2 GPUs == 1 GPU).
+                b.umma_tail = nullptr;
+                const int sms = net->num_sms;
+                // Measured: worth it for the 256 x 256 tiles (block 7: 1.98 -> 1.89 ms); 128 x 256 tiles cut any
+                // finer become L2-bandwidth bound and the tail costs as much as the wave it replaces.
+                if (!fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
+                    !getenv("DNNB_NO_TAIL")) {
+                    const int main_m = (tiles / sms) * sms / p.num_n_tiles;           // whole m-tiles in the full waves
+                    const int rows_left = p.M_total - main_m * mt * umma_conv::kBM;
+                    const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
+                    const double main_cost = 1.0;                                       // one main tile
+                    double best = 1e30;
+                    for (int bn_t : {128, 64}) {
+                        if (bn_t >= bn * mt || ocp % bn_t != 0) continue;
+                        UmmaKey kt{in_bf16, b.out_bf16, bn_t, swz, kbs, true, false, 1, false};
+                        const UmmaEntry *et = find_umma(kt);
+                        if (!et) continue;
+                        const int t_tiles = m_left * (ocp / bn_t);
+                        const double cost = (double)((t_tiles + sms - 1) / sms) * bn_t / (double)(bn * mt) * (bn_t < 128 ? 1.5 : 1.0);
+                        if (cost < best && cost < 0.8 * main_cost) {
+                            best = cost;
+                            b.umma_tail = et;
+                            b.up_tail = p;
+                            b.up_tail.m_base = main_m * mt * umma_conv::kBM;
+                            b.up_tail.num_m_tiles = m_left;
+                            b.up_tail.num_n_tiles = ocp / bn_t;
+                            b.grid_tail = t_tiles < sms ? t_tiles : sms;
+                        }
+                    }
+                    if (b.umma_tail) p.num_m_tiles = main_m;
+                }
             }
         }
     }
@@ -687,6 +731,11 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
             p.split_target = ++b.split_gen * p.splits;
         }
         CK(b.umma->launch(b.map_a, b.map_b, p, p.splits > 1 ? -b.grid : b.grid, st));
+        if (b.umma_tail) {
+            umma_conv::Params q = b.up_tail;
+            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
+            CK(b.umma_tail->launch(b.map_a, b.map_b_tail, q, b.grid_tail, st));
+        }
     }
     if (b.pool_separate) {
         simt::PoolParams q{};
@@ -1024,6 +1073,10 @@ int dnnb_net_finalize(dnnb_net *net) {
                 CK(cudaMemcpy(b.d_wpack, pk.data(), n * 4, cudaMemcpyHostToDevice));
             }
             if (encode_map_b(b)) return 1;
+            if (b.umma_tail) {
+                if (encode_map_b(b, &b.map_b_tail, b.umma_tail->key.bn)) return 1;
+                net->launches += 1;
+            }
             if (b.up.splits > 1) {
                 const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
                 const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
