@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libdnn_b200.so")
 
 TF32, BF16, FP32 = 0, 1, 2
 PRECISIONS = {"tf32": TF32, "bf16": BF16, "fp32": FP32}
-KERNEL_NAMES = {0: "simt", 1: "umma_tiled_pool", 2: "umma_im2col", 3: "umma_conv0", 4: "umma_rowpair"}
+KERNEL_NAMES = {0: "simt", 1: "umma_tiled_pool", 2: "umma_im2col", 3: "umma_conv0", 4: "umma_rowpair", 5: "umma_pair"}
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(LIB_PATH + " is missing: build it with `python dnn-inference-engine_b200/build.py` "

@@ -18,6 +18,7 @@
 
 #include "../../include/dnn_b200.h"
 #include "conv0_umma.cuh"
+#include "conv_pair.cuh"
 #include "conv_rowpair.cuh"
 #include "conv_umma.cuh"
 #include "ops_simt.cuh"
@@ -227,6 +228,38 @@ const UmmaEntry *find_umma(const UmmaKey &k) {
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-pair kernel instantiations (conv_pair.cuh): tcgen05.mma.cta_group::2 for the long-K 13x13 blocks
+typedef cudaError_t (*PairLauncher)(const CUtensorMap &, const CUtensorMap &, const pairconv::Params &, int grid,
+                                    cudaStream_t);
+struct PairEntry {
+    bool bf16, out_bf16;
+    int mt;
+    PairLauncher launch;
+    int stages;
+};
+template <bool BF16, bool OUT_BF16, int MT>
+cudaError_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const pairconv::Params &p, int grid, cudaStream_t st) {
+    using C = pairconv::Cfg<MT>;
+    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT>;
+    static bool done[64] = {};
+    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, pairconv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
+    return cudaGetLastError();
+}
+#define PAIR_ENTRY(BF16, OBF, MT) {BF16, OBF, MT, &launch_pair<BF16, OBF, MT>, pairconv::Cfg<MT>::STAGES}
+const PairEntry g_pair_table[] = {
+    PAIR_ENTRY(false, false, 1), PAIR_ENTRY(false, false, 2),
+    PAIR_ENTRY(true, true, 1),   PAIR_ENTRY(true, true, 2),
+    PAIR_ENTRY(true, false, 1),  PAIR_ENTRY(true, false, 2),
+};
+const PairEntry *find_pair(bool bf16, bool out_bf16, int mt) {
+    for (const PairEntry &e : g_pair_table)
+        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt) return &e;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
 // patch-resident row-pair kernel instantiations (conv_rowpair.cuh)
 typedef cudaError_t (*RowpairLauncher)(const CUtensorMap &, const CUtensorMap &, const rowpair::Params &, int grid,
                                        cudaStream_t);
@@ -295,6 +328,9 @@ struct Block {
     CUtensorMap map_a{}, map_b{};
     // tail launch (im2col blocks whose tile count is not a whole number of waves): the rows left after
     // the last full wave, in finer tiles (smaller BN, MT = 1) so that they spread over all SMs
+    const PairEntry *pair = nullptr;     // main launch on CTA pairs (cta_group::2) instead of b.umma
+    pairconv::Params pp{};
+    CUtensorMap map_b_pair{};            // weights map with a 128-row box: each CTA of a pair loads half a B tile
     const UmmaEntry *umma_tail = nullptr;
     CUtensorMap map_b_tail{};
     umma_conv::Params up_tail{};
@@ -588,39 +624,79 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 }
                 const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;
-                // Wave quantisation: 1352 tiles on 148 SMs are 9.14 waves and cost 10.  Cut the block into a
-                // main launch of whole waves and a tail launch over the remaining rows with tiles small
-                // enough to occupy every SM once.  Every output element still sums its K blocks in the same
-                // order, so results do not change (tests: batch invariance, 2 GPUs == 1 GPU).
+                // CTA pairs (conv_pair.cuh, tcgen05.mma.cta_group::2) for the big im2col blocks: a third to a
+                // quarter less L2->SMEM traffic per flop.  The main launch covers whole waves of pair tiles;
+                // the remaining rows go to a tail launch of the single-CTA kernel in 128 x 128 tiles.
+                b.pair = nullptr;
                 b.umma_tail = nullptr;
                 const int sms = net->num_sms;
+                const long k_total = (long)b.kh * b.kw * b.ic;
+                if (!fuse && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
+                    sms % 2 == 0 && !getenv("DNNB_NO_PAIR")) {
+                    // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
+                    // MT = 2 everywhere 82.8 k, no pairs 82.5 k -- two accumulator stages and six smem stages are
+                    // worth more than the last quarter of traffic
+                    int pmt = 1;
+                    if (getenv("DNNB_PAIR_MT")) pmt = atoi(getenv("DNNB_PAIR_MT")) == 2 ? 2 : 1;
+                    const PairEntry *pe = find_pair(in_bf16, b.out_bf16, pmt);
+                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
+                    const UmmaEntry *et = find_umma(kt);
+                    const int pairs = sms / 2;
+                    const int rows_per = 2 * pmt * umma_conv::kBM;
+                    const int m_all = p.M_total / rows_per;                 // whole pair tiles
+                    const int tiles_p = m_all * p.num_n_tiles;
+                    const int min_tiles = getenv("DNNB_PAIR_MIN_TILES") ? atoi(getenv("DNNB_PAIR_MIN_TILES")) : 2 * pairs;
+                    if (pe && et && tiles_p >= min_tiles && tiles_p > 0) {
+                        // stop at the last full wave when the partial one would be less than half full
+                        int main_m = m_all;
+                        if (tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs && !getenv("DNNB_PAIR_NO_TAIL")) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
+                        b.pair = pe;
+                        pairconv::Params &q = b.pp;
+                        q = pairconv::Params{};
+                        q.H = b.ih; q.W = b.iw; q.B = net->B; q.OC = b.oc;
+                        q.KH = b.kh; q.KW = b.kw; q.PT = b.pt; q.PL = b.pl;
+                        q.c_chunks = c_chunks;
+                        q.num_m_tiles = main_m; q.num_n_tiles = p.num_n_tiles;
+                        q.M_total = p.M_total; q.m_base = 0;
+                        q.leaky = b.leaky; q.round_tf32 = b.round_tf32;
+                        const int t = main_m * p.num_n_tiles;
+                        b.grid = 2 * (t < pairs ? t : pairs);
+                        const int rows_left = p.M_total - main_m * rows_per;
+                        if (rows_left > 0) {
+                            const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
+                            b.umma_tail = et;
+                            b.up_tail = p;
+                            b.up_tail.m_base = main_m * rows_per;
+                            b.up_tail.num_m_tiles = m_left;
+                            b.up_tail.num_n_tiles = ocp / 128;
+                            const int tt = m_left * (ocp / 128);
+                            b.grid_tail = tt < sms ? tt : sms;
+                        }
+                    }
+                }
+                // Without pairs: wave quantisation.  1352 tiles on 148 SMs are 9.14 waves and cost 10.  Cut the
+                // block into a main launch of whole waves and a tail launch over the remaining rows with tiles
+                // small enough to occupy every SM once.  Every output element still sums its K blocks in the same
+                // order, so results do not change (tests: batch invariance, 2 GPUs == 1 GPU).
                 // Measured: worth it for the 256 x 256 tiles (block 7: 1.98 -> 1.89 ms); 128 x 256 tiles cut any
                 // finer become L2-bandwidth bound and the tail costs as much as the wave it replaces.
-                if (!fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
+                if (!b.pair && !fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
                     !getenv("DNNB_NO_TAIL")) {
                     const int main_m = (tiles / sms) * sms / p.num_n_tiles;           // whole m-tiles in the full waves
                     const int rows_left = p.M_total - main_m * mt * umma_conv::kBM;
                     const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
-                    const double main_cost = 1.0;                                       // one main tile
-                    double best = 1e30;
-                    for (int bn_t : {128, 64}) {
-                        if (bn_t >= bn * mt || ocp % bn_t != 0) continue;
-                        UmmaKey kt{in_bf16, b.out_bf16, bn_t, swz, kbs, true, false, 1, false};
-                        const UmmaEntry *et = find_umma(kt);
-                        if (!et) continue;
-                        const int t_tiles = m_left * (ocp / bn_t);
-                        const double cost = (double)((t_tiles + sms - 1) / sms) * bn_t / (double)(bn * mt) * (bn_t < 128 ? 1.5 : 1.0);
-                        if (cost < best && cost < 0.8 * main_cost) {
-                            best = cost;
-                            b.umma_tail = et;
-                            b.up_tail = p;
-                            b.up_tail.m_base = main_m * mt * umma_conv::kBM;
-                            b.up_tail.num_m_tiles = m_left;
-                            b.up_tail.num_n_tiles = ocp / bn_t;
-                            b.grid_tail = t_tiles < sms ? t_tiles : sms;
-                        }
+                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
+                    const UmmaEntry *et = find_umma(kt);
+                    const int t_tiles = m_left * (ocp / 128);
+                    if (et && 128 < bn * mt && ocp % 128 == 0 && t_tiles <= sms) {
+                        b.umma_tail = et;
+                        b.up_tail = p;
+                        b.up_tail.m_base = main_m * mt * umma_conv::kBM;
+                        b.up_tail.num_m_tiles = m_left;
+                        b.up_tail.num_n_tiles = ocp / 128;
+                        b.grid_tail = t_tiles;
+                        p.num_m_tiles = main_m;
                     }
-                    if (b.umma_tail) p.num_m_tiles = main_m;
                 }
             }
         }
@@ -730,7 +806,13 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
             }
             p.split_target = ++b.split_gen * p.splits;
         }
-        CK(b.umma->launch(b.map_a, b.map_b, p, p.splits > 1 ? -b.grid : b.grid, st));
+        if (b.pair) {
+            pairconv::Params q = b.pp;
+            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out;
+            if (q.num_m_tiles > 0) CK(b.pair->launch(b.map_a, b.map_b_pair, q, b.grid, st));
+        } else {
+            CK(b.umma->launch(b.map_a, b.map_b, p, p.splits > 1 ? -b.grid : b.grid, st));
+        }
         if (b.umma_tail) {
             umma_conv::Params q = b.up_tail;
             q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
@@ -1077,6 +1159,7 @@ int dnnb_net_finalize(dnnb_net *net) {
                 if (encode_map_b(b, &b.map_b_tail, b.umma_tail->key.bn)) return 1;
                 net->launches += 1;
             }
+            if (b.pair && encode_map_b(b, &b.map_b_pair, pairconv::kBN / 2)) return 1;
             if (b.up.splits > 1) {
                 const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
                 const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
@@ -1493,14 +1576,14 @@ int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
     if (check_net(net, true)) return 1;
     if (block < 0 || block >= (int)net->blocks.size() || !info) return fail("bad block index or buffer");
     const Block &b = net->blocks[block];
-    info[0] = b.family; info[1] = b.oh; info[2] = b.ow; info[3] = b.oc;
+    info[0] = b.pair ? DNNB_KERNEL_UMMA_PAIR : b.family; info[1] = b.oh; info[2] = b.ow; info[3] = b.oc;
     info[4] = b.pool_fused ? 1 : 0;
     info[5] = b.bn; info[6] = b.swz;
-    info[7] = b.umma ? b.umma->stages : b.rowpair ? b.rowpair->stages : b.family == DNNB_KERNEL_UMMA_CONV0 ? conv0::kStages : 0;
+    info[7] = b.pair ? b.pair->stages : b.umma ? b.umma->stages : b.rowpair ? b.rowpair->stages : b.family == DNNB_KERNEL_UMMA_CONV0 ? conv0::kStages : 0;
     info[8] = b.grid;
     info[9] = b.pool_separate ? 1 : 0;
     info[10] = b.out_bf16 ? 2 : 4;
-    info[11] = 1 + (b.pool_separate ? 1 : 0);
+    info[11] = 1 + (b.pool_separate ? 1 : 0) + (b.umma_tail ? 1 : 0);
     return 0;
 }
 

@@ -43,6 +43,7 @@ typedef struct dnnb_net dnnb_net; /* opaque network handle */
 #define DNNB_KERNEL_UMMA_TILED 1 /* tcgen05 implicit GEMM, TMA tiled boxes, fused 2x2/2 pool */
 #define DNNB_KERNEL_UMMA_IM2COL 2 /* tcgen05 implicit GEMM, TMA im2col loads     */
 #define DNNB_KERNEL_UMMA_ROWPAIR 4 /* tcgen05, patch-resident row-pair tiles, resident weights, fused pool */
+#define DNNB_KERNEL_UMMA_PAIR 5 /* tcgen05.mma.cta_group::2: CTA pairs share each weight tile (im2col blocks, big batches) */
 #define DNNB_KERNEL_UMMA_CONV0 3 /* tcgen05, 3-channel first layer from the raw image, patch-resident, fused pool */
 
 const char *dnnb_last_error(void);

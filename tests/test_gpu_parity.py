@@ -258,6 +258,39 @@ def test_batch_results_do_not_depend_on_batch_size(oracle_libs):
     eng5.close(); eng1.close()
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_cta_pair_kernel_equals_the_single_cta_kernel_bit_for_bit(oracle_libs, monkeypatch, precision):
+    """Blocks 5-7 on CTA pairs (tcgen05.mma.cta_group::2, conv_pair.cuh).  The planner only uses pairs
+    at large batches; DNNB_PAIR_MIN_TILES=1 forces them at batch 13 (2197 rows: 8 whole 256-row pair tiles
+    plus a ragged tail launch), both tile heights.  Every K block is summed in the same order as in
+    the single-CTA kernel, so the outputs must be identical, and within tolerance of the oracle."""
+    B = 13
+    x = make_images(B, seed=400)
+
+    def run(env):
+        for k in ("DNNB_NO_PAIR", "DNNB_PAIR_MT", "DNNB_PAIR_MIN_TILES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = _yolo_engine(B, precision)
+        out = eng.run(x).copy()
+        plan = [p["kernel"] for p in eng.kernel_plan()]
+        blocks = [eng._net.block_output(i) for i in (5, 6, 7)]
+        eng.close()
+        return out, plan, blocks
+
+    ref_out, ref_plan, ref_blocks = run({"DNNB_NO_PAIR": "1"})
+    assert "umma_pair" not in ref_plan
+    for mt in ("1", "2"):
+        out, plan, blocks = run({"DNNB_PAIR_MIN_TILES": "1", "DNNB_PAIR_MT": mt})
+        assert plan[5:8] == ["umma_pair"] * 3, plan
+        for a, b in zip(blocks, ref_blocks):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(out, ref_out)
+    ref = chain.yolo_forward(make_weights(0), x[12:13], "oracle")
+    assert normalised_error(ref_out[12:13], ref) < TOL[precision]
+
+
 def test_full_size_batch256_properties(oracle_libs):
     """BASELINE configs[2] size.  Size-independent checks: sampled images match the batch-1
     engine bit for bit and the oracle within tolerance; no NaN/Inf anywhere."""
@@ -266,6 +299,7 @@ def test_full_size_batch256_properties(oracle_libs):
     eng = _yolo_engine(B, "tf32")
     out = eng.run(x)
     assert out.shape == (B, 13, 13, 125) and np.isfinite(out).all()
+    assert [p["kernel"] for p in eng.kernel_plan()][5:8] == ["umma_pair"] * 3     # CTA pairs at this size
     eng1 = _yolo_engine(1, "tf32")
     for i in (0, 127, 255):
         np.testing.assert_array_equal(eng1.run(x[i:i + 1])[0], out[i])
