@@ -156,17 +156,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ patch producers
-        // 340 groups of 4 pixels per patch; thread handles groups tid, tid + 256.  The group ->
-        // (patch row, column group) split does not depend on the tile: hoist it.
-        int g_row[kRounds], g_dst[kRounds], g_px[kRounds], g_src[kRounds];
+        // One pixel per lane: 1360 patch pixels, thread handles pixels tid, tid + 256, ...  Lane L of a warp
+        // then writes the 16-byte unit of pixel base + L, i.e. a warp store covers 512 contiguous bytes in the
+        // minimum of 4 shared-memory wavefronts (writing a 4-pixel group per thread, lanes 64 bytes apart,
+        // cost 16: measured, more than half of all the kernel's shared-memory wavefronts were store
+        // conflicts), and its three 4-byte loads at a 12-byte lane stride are conflict-free too.
+        // The pixel -> (patch row, column) split does not depend on the tile: hoist it.
+        constexpr int kPx = kPatchRows * kPatchPx;                               // 1360
+        constexpr int kPxRounds = (kPx + kProducerWarps * 32 - 1) / (kProducerWarps * 32);   // 6
+        int px_row[kPxRounds], px_col[kPxRounds], px_src[kPxRounds];
 #pragma unroll
-        for (int it = 0; it < kRounds; ++it) {
-            const int g = threadIdx.x + kProducerWarps * 32 * it;
-            const int r = g / kGroups, gx = g - r * kGroups;
-            g_row[it] = g < kTileGroups ? r : 1 << 20;              // invalid groups fail the row test below
-            g_px[it] = 4 * gx - 4;
-            g_dst[it] = r * kPatchRowBytes + gx * 64;
-            g_src[it] = IN_U8 ? r * kRawRowBytesU8 + (4 * gx - 4 + kRawLeadU8) * 3 : g * 48;
+        for (int it = 0; it < kPxRounds; ++it) {
+            const int i = threadIdx.x + kProducerWarps * 32 * it;
+            const int r = i / kPatchPx, x = i - r * kPatchPx;
+            px_row[it] = i < kPx ? r : 1 << 20;                     // pixels past the patch fail the row test below
+            px_col[it] = x - 4;
+            px_src[it] = IN_U8 ? r * kRawRowBytesU8 + (x - 4 + kRawLeadU8) * 3 : i * 12;
         }
         Coord tc = decode(tile_begin);
         for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
@@ -174,61 +179,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             const int slot = t % kRawDepth, stage = t % kStages;
             ptx::mbar_wait(bar_rfull + 8 * slot, (t / kRawDepth) & 1);        // raw pixels have landed
             ptx::mbar_wait(bar_empty + 8 * stage, ((t / kStages) & 1) ^ 1);    // patch slot is free
-            uint8_t *patch = s_patch + stage * kPatchBytes;
+            uint4 *patch = reinterpret_cast<uint4 *>(s_patch + stage * kPatchBytes);
             const uint8_t *raw = s_raw + slot * kRawBytes;
 #pragma unroll
-            for (int it = 0; it < kRounds; ++it) {
-                if (g_row[it] < kPatchRows) {
-                    const bool ok = (unsigned)(row0 + g_row[it]) < (unsigned)p.H && (unsigned)(w0 + g_px[it]) < (unsigned)p.W;
-                    uint4 *dst = reinterpret_cast<uint4 *>(patch + g_dst[it]);
-                    if constexpr (IN_U8) {
-                        // 4 pixels = 12 bytes; the table holds the finished operand bits of float32(v / 255.)
-                        uint32_t w3[3] = {0u, 0u, 0u};
-                        if (ok) {
-                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + g_src[it]);
-                            w3[0] = src[0]; w3[1] = src[1]; w3[2] = src[2];
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t v[3];
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const int byte = 3 * q + c;
-                                v[c] = s_lut[(w3[byte >> 2] >> (8 * (byte & 3))) & 0xffu];
-                            }
-                            const uint32_t c0 = p.swap_rb ? v[2] : v[0], c2 = p.swap_rb ? v[0] : v[2];
-                            uint4 o;
-                            if constexpr (BF16) { o.x = c0 | (v[1] << 16); o.y = c2; o.z = 0u; o.w = 0u; }
-                            else { o.x = c0; o.y = v[1]; o.z = c2; o.w = 0u; }
-                            if (!ok) o = make_uint4(0u, 0u, 0u, 0u);      // outside the image: zeros (SAME padding)
-                            dst[q] = o;
-                        }
-                        continue;
-                    }
-                    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, c = a;      // outside the image: zeros (SAME padding)
+            for (int it = 0; it < kPxRounds; ++it) {
+                if (px_row[it] < kPatchRows) {
+                    const bool ok = (unsigned)(row0 + px_row[it]) < (unsigned)p.H && (unsigned)(w0 + px_col[it]) < (unsigned)p.W;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);                        // outside the image: zeros (SAME padding)
                     if (ok) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(raw + g_src[it]);
-                        a = src[0]; b = src[1]; c = src[2];
-                    }
-                    const uint32_t f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 o;
-                        if constexpr (BF16) {
-                            __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f[3 * q]), __uint_as_float(f[3 * q + 1]));
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(f[3 * q + 2]), 0.f);
-                            o.x = *reinterpret_cast<uint32_t *>(&rg);
-                            o.y = *reinterpret_cast<uint32_t *>(&b0);
-                            o.z = 0u; o.w = 0u;
+                        if constexpr (IN_U8) {
+                            // the table holds the finished operand bits of float32(v / 255.)
+                            const uint8_t *src = raw + px_src[it];
+                            const uint32_t v0 = s_lut[src[0]], v1 = s_lut[src[1]], v2 = s_lut[src[2]];
+                            const uint32_t c0 = p.swap_rb ? v2 : v0, c2 = p.swap_rb ? v0 : v2;
+                            if constexpr (BF16) { o.x = c0 | (v1 << 16); o.y = c2; }
+                            else { o.x = c0; o.y = v1; o.z = c2; }
                         } else {
-                            // round to nearest TF32: add half an ulp; the MMA drops the low 13 bits itself
-                            o.x = ok ? f[3 * q] + 0x1000u : 0u;
-                            o.y = ok ? f[3 * q + 1] + 0x1000u : 0u;
-                            o.z = ok ? f[3 * q + 2] + 0x1000u : 0u;
-                            o.w = 0u;
+                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + px_src[it]);
+                            const uint32_t f0 = src[0], f1 = src[1], f2 = src[2];
+                            if constexpr (BF16) {
+                                __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f0), __uint_as_float(f1));
+                                __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(f2), 0.f);
+                                o.x = *reinterpret_cast<uint32_t *>(&rg);
+                                o.y = *reinterpret_cast<uint32_t *>(&b0);
+                            } else {
+                                // round to nearest TF32: add half an ulp; the MMA drops the low 13 bits itself
+                                o.x = f0 + 0x1000u; o.y = f1 + 0x1000u; o.z = f2 + 0x1000u;
+                            }
                         }
-                        dst[q] = o;
                     }
+                    patch[threadIdx.x + kProducerWarps * 32 * it] = o;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
