@@ -29,7 +29,6 @@ namespace pairconv {
 
 constexpr int kThreads = 192;
 constexpr int kBM = 128;
-constexpr int kBN = 256;
 constexpr int kSwz = 128;
 
 struct Params {
@@ -46,7 +45,9 @@ struct Params {
     int leaky, round_tf32;
 };
 
-template <int MT>
+// kBN = output channels per pair tile (256; 128 for the tail launch over a block's last rows, so that
+// they spread over twice as many pairs)
+template <int MT, int kBN = 256>
 struct Cfg {
     static constexpr int A_TILE = kBM * kSwz;
     static constexpr int B_HALF = (kBN / 2) * kSwz;
@@ -57,13 +58,14 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES + 1024;
     static constexpr int ACC_COLS = MT * kBN;
     static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM allocation");
 };
 
-template <bool BF16, bool OUT_BF16, int MT>
+template <bool BF16, bool OUT_BF16, int MT, int kBN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-    using C = Cfg<MT>;
+    using C = Cfg<MT, kBN>;
     constexpr int STAGES = C::STAGES;
     constexpr int ACC = C::ACC_STAGES;
     constexpr int ES = BF16 ? 2 : 4;

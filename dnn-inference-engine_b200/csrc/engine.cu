@@ -233,29 +233,29 @@ typedef cudaError_t (*PairLauncher)(const CUtensorMap &, const CUtensorMap &, co
                                     cudaStream_t);
 struct PairEntry {
     bool bf16, out_bf16;
-    int mt;
+    int mt, bn;
     PairLauncher launch;
     int stages;
 };
-template <bool BF16, bool OUT_BF16, int MT>
+template <bool BF16, bool OUT_BF16, int MT, int BN>
 cudaError_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const pairconv::Params &p, int grid, cudaStream_t st) {
-    using C = pairconv::Cfg<MT>;
-    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT>;
+    using C = pairconv::Cfg<MT, BN>;
+    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT, BN>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
     kern<<<grid, pairconv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
     return cudaGetLastError();
 }
-#define PAIR_ENTRY(BF16, OBF, MT) {BF16, OBF, MT, &launch_pair<BF16, OBF, MT>, pairconv::Cfg<MT>::STAGES}
+#define PAIR_ENTRY(BF16, OBF, MT, BN) {BF16, OBF, MT, BN, &launch_pair<BF16, OBF, MT, BN>, pairconv::Cfg<MT, BN>::STAGES}
 const PairEntry g_pair_table[] = {
-    PAIR_ENTRY(false, false, 1), PAIR_ENTRY(false, false, 2),
-    PAIR_ENTRY(true, true, 1),   PAIR_ENTRY(true, true, 2),
-    PAIR_ENTRY(true, false, 1),  PAIR_ENTRY(true, false, 2),
+    PAIR_ENTRY(false, false, 1, 256), PAIR_ENTRY(false, false, 2, 256), PAIR_ENTRY(false, false, 1, 128),
+    PAIR_ENTRY(true, true, 1, 256),   PAIR_ENTRY(true, true, 2, 256),   PAIR_ENTRY(true, true, 1, 128),
+    PAIR_ENTRY(true, false, 1, 256),  PAIR_ENTRY(true, false, 2, 256),  PAIR_ENTRY(true, false, 1, 128),
 };
-const PairEntry *find_pair(bool bf16, bool out_bf16, int mt) {
+const PairEntry *find_pair(bool bf16, bool out_bf16, int mt, int bn = 256) {
     for (const PairEntry &e : g_pair_table)
-        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt) return &e;
+        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt && e.bn == bn) return &e;
     return nullptr;
 }
 
@@ -331,6 +331,11 @@ struct Block {
     const PairEntry *pair = nullptr;     // main launch on CTA pairs (cta_group::2) instead of b.umma
     pairconv::Params pp{};
     CUtensorMap map_b_pair{};            // weights map with a 128-row box: each CTA of a pair loads half a B tile
+    // the last whole pair tiles of a block, past the full waves: pairs again, but 256 x 128 tiles (64-row B halves)
+    const PairEntry *pair_tail = nullptr;
+    pairconv::Params pp_tail{};
+    CUtensorMap map_b_pair_tail{};
+    int grid_pair_tail = 0;
     const UmmaEntry *umma_tail = nullptr;
     CUtensorMap map_b_tail{};
     umma_conv::Params up_tail{};
@@ -661,12 +666,28 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         q.leaky = b.leaky; q.round_tf32 = b.round_tf32;
                         const int t = main_m * p.num_n_tiles;
                         b.grid = 2 * (t < pairs ? t : pairs);
-                        const int rows_left = p.M_total - main_m * rows_per;
+                        int rows_done = main_m * rows_per;
+                        // whole pair tiles past the full waves: pairs again, in 256 x 128 tiles so that they
+                        // spread over twice as many pairs (block 7: 20 tiles -> 40 of the 74 pairs, 100 -> 50 us)
+                        b.pair_tail = nullptr;
+                        const PairEntry *pt = pmt == 1 ? find_pair(in_bf16, b.out_bf16, 1, 128) : nullptr;
+                        const int m_pt = (p.M_total - rows_done) / (2 * umma_conv::kBM);
+                        if (pt && m_pt > 0 && !getenv("DNNB_NO_PAIR_TAIL")) {
+                            b.pair_tail = pt;
+                            b.pp_tail = q;
+                            b.pp_tail.m_base = rows_done;
+                            b.pp_tail.num_m_tiles = m_pt;
+                            b.pp_tail.num_n_tiles = ocp / 128;
+                            const int tt = m_pt * (ocp / 128);
+                            b.grid_pair_tail = 2 * (tt < pairs ? tt : pairs);
+                            rows_done += m_pt * 2 * umma_conv::kBM;
+                        }
+                        const int rows_left = p.M_total - rows_done;
                         if (rows_left > 0) {
                             const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
                             b.umma_tail = et;
                             b.up_tail = p;
-                            b.up_tail.m_base = main_m * rows_per;
+                            b.up_tail.m_base = rows_done;
                             b.up_tail.num_m_tiles = m_left;
                             b.up_tail.num_n_tiles = ocp / 128;
                             const int tt = m_left * (ocp / 128);
@@ -810,6 +831,11 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
             pairconv::Params q = b.pp;
             q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out;
             if (q.num_m_tiles > 0) CK(b.pair->launch(b.map_a, b.map_b_pair, q, b.grid, st));
+            if (b.pair_tail) {
+                pairconv::Params t = b.pp_tail;
+                t.scale = b.d_scale; t.shift = b.d_shift; t.out = conv_out;
+                CK(b.pair_tail->launch(b.map_a, b.map_b_pair_tail, t, b.grid_pair_tail, st));
+            }
         } else {
             CK(b.umma->launch(b.map_a, b.map_b, p, p.splits > 1 ? -b.grid : b.grid, st));
         }
@@ -1159,7 +1185,11 @@ int dnnb_net_finalize(dnnb_net *net) {
                 if (encode_map_b(b, &b.map_b_tail, b.umma_tail->key.bn)) return 1;
                 net->launches += 1;
             }
-            if (b.pair && encode_map_b(b, &b.map_b_pair, pairconv::kBN / 2)) return 1;
+            if (b.pair && encode_map_b(b, &b.map_b_pair, 128)) return 1;
+            if (b.pair_tail) {
+                if (encode_map_b(b, &b.map_b_pair_tail, 64)) return 1;
+                net->launches += 1;
+            }
             if (b.up.splits > 1) {
                 const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
                 const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
@@ -1583,7 +1613,7 @@ int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
     info[8] = b.grid;
     info[9] = b.pool_separate ? 1 : 0;
     info[10] = b.out_bf16 ? 2 : 4;
-    info[11] = 1 + (b.pool_separate ? 1 : 0) + (b.umma_tail ? 1 : 0);
+    info[11] = 1 + (b.pool_separate ? 1 : 0) + (b.umma_tail ? 1 : 0) + (b.pair_tail ? 1 : 0);
     return 0;
 }
 
