@@ -32,10 +32,22 @@ constexpr int kMmaWarps = 2;      // tiles alternate between two issuing warps: 
 constexpr int kThreads = (1 + kMmaWarps + 8) * 32;
 constexpr int kPatchW = 130;      // 128 columns + left/right halo
 
+// LINEAR tiling (template flag): instead of 128-column tiles of the image (416, 208 and 104 columns are
+// 3.25, 1.63 and 0.81 such tiles: 19 % of the MMA rows are padding) a tile is 128 consecutive positions
+// of the sequence  (image, row group of TR rows, column position p in [0, W+4))  -- input columns
+// -3 .. W (zero outside the image), output column p - 2.  Plane s of the patch (input row TR j + s - 1 of
+// every row group j) is then one TMA *im2col* walk of 130 positions that wraps from one row group
+// to the next (traversal stride TR in H, bounding box [s-1, H-1+s-TR]), taps dj = 0..2 are still row
+// offsets into the plane, and a lane's rows of the tile are still the same column of consecutive
+// image rows, so the pooling does not change.  4 positions per row group are padding: 2-4 %.
+struct LinMaps {
+    CUtensorMap m[10];    // one per patch plane (TR + 2 <= 10)
+};
+
 struct Params {
     int B, H, W;          // conv output = input spatial size
     int col_tiles;        // ceil(W / 128)
-    int num_tiles;        // B * (H/TR) * col_tiles
+    int num_tiles;        // B * (H/TR) * col_tiles; LINEAR: ceil(B * (H/TR) * (W+4) / 128)
     const float *scale;   // [OC]
     const float *shift;   // [OC]
     void *out;            // [B, H/2, W/2, OC]
@@ -47,12 +59,15 @@ struct Params {
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
 
-template <int OC, int SWZ, int TR>
+template <int OC, int SWZ, int TR, bool LINEAR = false>
 struct Cfg {
     static constexpr int PATCH_ROWS = TR + 2;                  // output rows + top/bottom halo
-    static constexpr int PATCH_ROW = kPatchW * SWZ;
-    static constexpr int PATCH_RAW = PATCH_ROWS * PATCH_ROW;
-    static constexpr int PATCH_BYTES = (PATCH_RAW + 1023) / 1024 * 1024;
+    // pixels between patch planes: 130; LINEAR loads every plane with its own TMA request, whose
+    // destination must be 128-byte aligned (32-byte pixels: 132)
+    static constexpr int PITCH_PX = (LINEAR && (kPatchW * SWZ) % 128 != 0) ? kPatchW + 2 : kPatchW;
+    static constexpr int PATCH_ROW = PITCH_PX * SWZ;
+    static constexpr int PATCH_RAW = PATCH_ROWS * kPatchW * SWZ;   // bytes the TMA loads of one tile deliver
+    static constexpr int PATCH_BYTES = (PATCH_ROWS * PATCH_ROW + 1023) / 1024 * 1024;
     static constexpr int W_DJ_BYTES = 3 * OC * SWZ;            // one dj: rows [di=2 | di=1 | di=0] x OC
     static constexpr int W_BYTES = 3 * W_DJ_BYTES;
     static constexpr int TAIL_BYTES = 1024 + 2 * OC * 4;
@@ -71,11 +86,11 @@ struct Cfg {
     static_assert(OC % 16 == 0 && 3 * OC <= 256, "weights of one dj must fit one TMA box");
 };
 
-template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR>
+template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR, bool LINEAR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                    const Params p) {
-    using C = Cfg<OC, SWZ, TR>;
+                    const Params p, const __grid_constant__ LinMaps lin) {
+    using C = Cfg<OC, SWZ, TR, LINEAR>;
     constexpr int STAGES = C::STAGES, ACC = C::ACC_STAGES;
     constexpr int KC = SWZ / 32;                     // MMAs along K per tap (32 bytes of K each)
 
@@ -118,8 +133,13 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     };
 
+    const int P = p.W + 4;                // LINEAR: positions per row group
     if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&map_a);
+        if constexpr (LINEAR) {
+            for (int s = 0; s < C::PATCH_ROWS; ++s) ptx::prefetch_tensormap(&lin.m[s]);
+        } else {
+            ptx::prefetch_tensormap(&map_a);
+        }
         ptx::prefetch_tensormap(&map_w);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
         for (int s = 0; s < ACC; ++s) { ptx::mbar_init(bar_tfull + 8 * s, 1); ptx::mbar_init(bar_tempty + 8 * s, 128); }
@@ -143,8 +163,18 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int stage = t % STAGES;
                 ptx::mbar_wait(bar_empty + 8 * stage, ((t / STAGES) & 1) ^ 1);
                 ptx::mbar_expect_tx(bar_full + 8 * stage, C::PATCH_RAW);
-                ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, tc.ct * 128 - 1,
-                                 TR * tc.j - 1, tc.n);
+                if constexpr (LINEAR) {
+                    const int q0 = (tile_begin + t) * 128;                // first position of the tile (< 2^31: checked by the planner)
+                    const int rg = q0 / P, pos = q0 - rg * P;
+                    const int n = rg / rows2, j = rg - n * rows2;
+#pragma unroll
+                    for (int s = 0; s < C::PATCH_ROWS; ++s)
+                        ptx::tma_load_im2col_4d(patch_base + stage * C::PATCH_BYTES + s * C::PATCH_ROW, &lin.m[s],
+                                                bar_full + 8 * stage, 0, pos - 3, TR * j + s - 1, n, 0, 0);
+                } else {
+                    ptx::tma_load_4d(patch_base + stage * C::PATCH_BYTES, &map_a, bar_full + 8 * stage, 0, tc.ct * 128 - 1,
+                                     TR * tc.j - 1, tc.n);
+                }
             }
         }
     } else if (warp <= kMmaWarps) {
@@ -182,7 +212,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int dj = 0; dj < 3; ++dj) {
 #pragma unroll
                         for (int k = 0; k < KC; ++k) {
-                            const uint32_t a_off = ((r * kPatchW + dj) * SWZ + 32 * k) >> 4;
+                            const uint32_t a_off = ((r * C::PITCH_PX + dj) * SWZ + 32 * k) >> 4;
                             const uint32_t b_off = (dj * C::W_DJ_BYTES + wrow * SWZ + 32 * k) >> 4;
                             ptx::umma<BF16>(dcol, ptx::umma_desc_join(a_lo0 + a_off, HI), ptx::umma_desc_join(b_lo0 + b_off, HI),
                                             idesc, (oi >= NINIT || dj != 0 || k != 0) ? 1u : 0u);
@@ -202,12 +232,22 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const bool odd = lane & 1;
         Coord tc = decode(tile_begin + group);
         for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
-            const int ct = tc.ct, j = tc.j, n = tc.n;
-            const int w = ct * 128 + m;
+            int ct = tc.ct, j = tc.j, n = tc.n;
+            int w = ct * 128 + m;
+            bool live = ct * 128 + quarter * 32 < p.W;     // warp-uniform: skip quarters right of the image
+            if constexpr (LINEAR) {
+                const int q = (tile_begin + t) * 128 + m;
+                const int rg = q / P;
+                n = rg / rows2;
+                j = rg - n * rows2;
+                w = q - rg * P - 2;                        // output column; the 4 pad positions of a row group fail 0 <= w < W
+                if (n >= p.B) w = -1;
+                live = true;
+            }
             const int acc = t % ACC;
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
             ptx::tc_fence_after();
-            if (ct * 128 + quarter * 32 < p.W) {           // warp-uniform: skip quarters right of the image
+            if (live) {
 #pragma unroll 1
                 for (int rp = 0; rp < TR / 2; ++rp) {                  // pooling row pairs of the tile
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + 2 * rp * OC;
@@ -220,7 +260,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // second row
                     ptx::tmem_ld_wait();
                     float v[16];
-                    if (p.prepool != nullptr && w < p.W) {     // debug dump of the pooled-over activations (cold path)
+                    if (p.prepool != nullptr && (unsigned)w < (unsigned)p.W) {     // debug dump of the pooled-over activations (cold path)
                         for (int c = 0; c < 16; ++c) {
                             const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
                             float a = fmaf(__uint_as_float(top[c]), sc, sh);
@@ -273,7 +313,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
                         }
                     }
-                    if (w < p.W) {
+                    if ((unsigned)w < (unsigned)p.W) {
                         const size_t off = pix * OC + c0 + (odd ? 8 : 0);
                         if constexpr (OUT_BF16) {
                             __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);

@@ -261,28 +261,30 @@ const PairEntry *find_pair(bool bf16, bool out_bf16, int mt, int bn = 256) {
 
 // ------------------------------------------------------------------------------------------
 // patch-resident row-pair kernel instantiations (conv_rowpair.cuh)
-typedef cudaError_t (*RowpairLauncher)(const CUtensorMap &, const CUtensorMap &, const rowpair::Params &, int grid,
-                                       cudaStream_t);
+typedef cudaError_t (*RowpairLauncher)(const CUtensorMap &, const CUtensorMap &, const rowpair::Params &,
+                                       const rowpair::LinMaps &, int grid, cudaStream_t);
 struct RowpairEntry {
     bool bf16, out_bf16;
     int oc, swz, tr;        // tr = output rows per tile
-    RowpairLauncher launch;
+    RowpairLauncher launch;         // 128-column tiles of the image
+    RowpairLauncher launch_linear;  // tiles over the linearised (row group, column) positions
     int stages;
 };
 
-template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR>
-cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const rowpair::Params &p, int grid,
-                           cudaStream_t st) {
-    using C = rowpair::Cfg<OC, SWZ, TR>;
-    auto kern = rowpair::conv_rowpair_kernel<BF16, OUT_BF16, OC, SWZ, TR>;
+template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR, bool LINEAR>
+cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const rowpair::Params &p,
+                           const rowpair::LinMaps &lin, int grid, cudaStream_t st) {
+    using C = rowpair::Cfg<OC, SWZ, TR, LINEAR>;
+    auto kern = rowpair::conv_rowpair_kernel<BF16, OUT_BF16, OC, SWZ, TR, LINEAR>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
-    kern<<<grid, rowpair::kThreads, C::SMEM_BYTES, st>>>(ma, mw, p);
+    kern<<<grid, rowpair::kThreads, C::SMEM_BYTES, st>>>(ma, mw, p, lin);
     return cudaGetLastError();
 }
-#define ROWPAIR_ENTRY(BF16, OBF, OC, SWZ, TR) \
-    {BF16, OBF, OC, SWZ, TR, &launch_rowpair<BF16, OBF, OC, SWZ, TR>, rowpair::Cfg<OC, SWZ, TR>::STAGES}
+#define ROWPAIR_ENTRY(BF16, OBF, OC, SWZ, TR)                                                             \
+    {BF16, OBF, OC, SWZ, TR, &launch_rowpair<BF16, OBF, OC, SWZ, TR, false>, &launch_rowpair<BF16, OBF, OC, SWZ, TR, true>, \
+     rowpair::Cfg<OC, SWZ, TR>::STAGES}
 // per shape in order of preference (measured on B200, batch 512): 4-row tiles win for 16->32 channels
 // (TF32 0.487 -> 0.468 ms, BF16 0.454 -> 0.396 ms; 8 rows leave too few patch stages), 2 rows for 32->64;
 // the planner takes the first entry whose TR divides the image height
@@ -328,6 +330,8 @@ struct Block {
     CUtensorMap map_a{}, map_b{};
     // tail launch (im2col blocks whose tile count is not a whole number of waves): the rows left after
     // the last full wave, in finer tiles (smaller BN, MT = 1) so that they spread over all SMs
+    bool rp_linear = false;              // row-pair kernel: tiles over linearised positions (conv_rowpair.cuh LINEAR)
+    rowpair::LinMaps lin_maps{};
     const PairEntry *pair = nullptr;     // main launch on CTA pairs (cta_group::2) instead of b.umma
     pairconv::Params pp{};
     CUtensorMap map_b_pair{};            // weights map with a 128-row box: each CTA of a pair loads half a B tile
@@ -423,6 +427,19 @@ int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
         r = g_encode_im2col(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper, (cuuint32_t)bkc,
                             (cuuint32_t)umma_conv::kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz),
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR && b.rp_linear) {
+        // one im2col map per patch plane s: base pixels w in [-3, W], h in {s-1, s-1+TR, ...} (H/TR of them),
+        // walked W-fastest, 130 positions per load (conv_rowpair.cuh, LINEAR)
+        const int tr = b.rowpair->tr;
+        cuuint32_t estr_lin[4] = {1, 1, (cuuint32_t)tr, 1};
+        r = CUDA_SUCCESS;
+        for (int s = 0; s < tr + 2 && r == CUDA_SUCCESS; ++s) {
+            int lower[2] = {-3, s - 1};
+            int upper[2] = {1, s - tr};
+            r = g_encode_im2col(&b.lin_maps.m[s], dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper,
+                                (cuuint32_t)b.ic, (cuuint32_t)rowpair::kPatchW, estr_lin, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
     } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
         cuuint32_t box[4] = {(cuuint32_t)b.ic, (cuuint32_t)rowpair::kPatchW, (cuuint32_t)(b.rowpair->tr + 2), 1};
         r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
@@ -536,6 +553,12 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
             r.B = net->B; r.H = b.ih; r.W = b.iw;
             r.col_tiles = (b.iw + 127) / 128;
             r.num_tiles = net->B * (b.ih / e->tr) * r.col_tiles;
+            // image widths that are a poor multiple of 128 columns (416/208/104: 19 % padding): tile the
+            // linearised positions instead (W + 4 per row group, 2-4 % padding)
+            const long lin_tiles = ((long)net->B * (b.ih / e->tr) * (b.iw + 4) + 127) / 128;
+            b.rp_linear = lin_tiles * 100 < (long)r.num_tiles * 95 && lin_tiles * 128 < (1L << 30) && !getenv("DNNB_NO_ROWPAIR_LINEAR");
+            if (getenv("DNNB_ROWPAIR_LINEAR")) b.rp_linear = atoi(getenv("DNNB_ROWPAIR_LINEAR")) != 0;
+            if (b.rp_linear) { r.num_tiles = (int)lin_tiles; r.col_tiles = 1; }
             r.leaky = b.leaky; r.round_tf32 = b.round_tf32;
             r.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
             b.grid = r.num_tiles < net->num_sms ? r.num_tiles : net->num_sms;
@@ -635,7 +658,6 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 b.pair = nullptr;
                 b.umma_tail = nullptr;
                 const int sms = net->num_sms;
-                const long k_total = (long)b.kh * b.kw * b.ic;
                 if (!fuse && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
                     sms % 2 == 0 && !getenv("DNNB_NO_PAIR")) {
                     // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
@@ -812,7 +834,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         }
         rowpair::Params p = b.rp;
         p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
-        CK(b.rowpair->launch(b.map_a, b.map_b, p, b.grid, st));
+        CK((b.rp_linear ? b.rowpair->launch_linear : b.rowpair->launch)(b.map_a, b.map_b, p, b.lin_maps, b.grid, st));
     } else {
         if (b.map_a_base != in) {
             if (encode_map_a(net, b, in)) return 1;
