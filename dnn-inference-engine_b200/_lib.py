@@ -59,6 +59,7 @@ _sig("dnnb_net_block_info", c_void_p, c_int, IP)
 _sig("dnnb_net_debug_prepool", c_void_p, c_int, FP)
 _sig("dnnb_net_time_blocks", c_void_p, c_int, c_int, FP)
 _sig("dnnb_net_launches_per_forward", c_void_p, IP)
+_sig("dnnb_net_debug_block_limit", c_void_p, c_int)
 _sig("dnnb_net_profile_block", c_void_p, c_int)
 _sig("dnnb_net_profile_read", c_void_p, FP, IP)
 _sig("dnnb_net_destroy", c_void_p)
@@ -81,7 +82,8 @@ EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
            "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
-           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
+           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit",
+           "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
            "dnnb_postprocess", "dnnb_postprocess_candidates", "dnnb_nms", "dnnb_net_set_detect",
            "dnnb_net_detect_async", "dnnb_net_detect_u8_async", "dnnb_net_detect_device",
@@ -292,6 +294,9 @@ class Net:
         ms, n = c_float(0), c_int(0)
         check(lib.dnnb_net_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def debug_block_limit(self, blocks):
+        check(lib.dnnb_net_debug_block_limit(self._h, blocks))
 
     def launches_per_forward(self):
         n = c_int(0)

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_tiles = p.H / kTileRows;
 
+    ptx::griddep_launch();
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(bar_full + 8 * s, kProducerWarps);
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();      // weights, constants and table are loaded; frames and the output buffer are stream-ordered
 
     const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_begin = (int)blockIdx.x * per_cta;

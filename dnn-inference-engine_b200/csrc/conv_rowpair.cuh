@@ -134,6 +134,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     };
 
     const int P = p.W + 4;                // LINEAR: positions per row group
+    ptx::griddep_launch();
     if (threadIdx.x == 0) {
         if constexpr (LINEAR) {
             for (int s = 0; s < C::PATCH_ROWS; ++s) ptx::prefetch_tensormap(&lin.m[s]);
@@ -152,12 +153,14 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp != 0) ptx::griddep_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (ptx::elect_one()) {
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);                 // resident weights, once
             for (int dj = 0; dj < 3; ++dj) ptx::tma_load_3d(w_base + dj * C::W_DJ_BYTES, &map_w, bar_w, 0, 0, dj);
+            ptx::griddep_wait();                                    // the activations are the preceding kernel's output
             Coord tc = decode(tile_begin);
             for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
                 const int stage = t % STAGES;

@@ -57,12 +57,12 @@ struct Params {
     // slab of `workspace`, bumps `counters[tile]` and waits until all `splits` slabs are there; then
     // every CTA sums a 1/splits share of the tile's rows over the slabs IN SLAB ORDER and runs the
     // epilogue on it: deterministic, no atomics on data.  All CTAs of the launch must be co-resident
-    // (grid = work items <= SMs, cooperative launch).  Counters only ever grow: launch number g waits
-    // for g * splits.
+    // (grid = work items <= SMs).  A tile has an arrival and a departure counter; the last CTA to leave
+    // the wait zeroes both, so every launch starts from zero without host bookkeeping (the launch sequence
+    // can be replayed from a CUDA graph).
     int splits;           // 1 = off
     float *workspace;     // [splits][num_m_tiles * MT * 128][num_n_tiles * BN] fp32
-    int *counters;        // [num_m_tiles * num_n_tiles]
-    int split_target;     // launch number * splits
+    int *counters;        // [num_m_tiles * num_n_tiles][2]: arrived, departed; zero between launches
 };
 
 // MT = M tiles (of 128 rows) per CTA tile that share every B tile: MT = 2 turns the CTA tile
@@ -132,6 +132,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ks_hi = (int)((long)num_kstages * (split + 1) / p.splits);
     };
 
+    ptx::griddep_launch();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -146,20 +147,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
-    for (int i = threadIdx.x; i < p.num_n_tiles * BN; i += kThreads) {
-        s_scale[i] = p.scale[i];
-        s_shift[i] = p.shift[i];
+    {   // epilogue constants: a CTA with a single work item only needs the columns of its own N tile
+        const bool one_tile = num_tiles <= (int)gridDim.x;
+        const int c_lo = one_tile ? ((int)blockIdx.x % p.num_n_tiles) * BN : 0;
+        const int c_hi = one_tile ? c_lo + BN : p.num_n_tiles * BN;
+        for (int i = c_lo + threadIdx.x; i < c_hi; i += kThreads) {
+            s_scale[i] = p.scale[i];
+            s_shift[i] = p.shift[i];
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: up to here nothing depends on the preceding kernel.  The producer
+    // lane additionally starts the weight tiles of its first stages before it waits.
+    if (warp != 0) ptx::griddep_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            // weights do not depend on the preceding kernel: arm the first ring pass and start its B tiles
+            // before waiting for that kernel (the first pass over the ring finds every slot empty)
+            int early = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                int ks_lo, ks_hi;
+                k_range(blockIdx.x, ks_lo, ks_hi);
+                early = ks_hi - ks_lo < STAGES ? ks_hi - ks_lo : STAGES;
+                const int n_tile = (int)blockIdx.x % p.num_n_tiles;
+                for (int e = 0; e < early; ++e) {
+                    const uint32_t full = bar_full + 8 * e;
+                    ptx::mbar_expect_tx(full, C::STAGE_BYTES);
+                    const uint32_t sb = smem_base + e * C::STAGE_BYTES + KBS * MT * C::A_TILE;
+#pragma unroll
+                    for (int j = 0; j < KBS; ++j) {
+                        const int kb = (ks_lo + e) * KBS + j;
+                        const int tap = kb / p.c_chunks;
+                        ptx::tma_load_4d(sb + j * C::B_TILE, &map_b, full, 0, n_tile * BN, kb - tap * p.c_chunks, tap);
+                    }
+                }
+            }
+            ptx::griddep_wait();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.num_n_tiles;
                 const int m_tile = (tile % tiles_mn) / p.num_n_tiles;
@@ -184,9 +214,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
                 for (int ks = ks_lo; ks < ks_hi; ++ks) {
-                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const bool armed = early > 0;        // slot armed and its B tiles in flight since before the wait
+                    if (armed) --early;
+                    else ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    ptx::mbar_expect_tx(full, C::STAGE_BYTES);
+                    if (!armed) ptx::mbar_expect_tx(full, C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t sb = sa + KBS * MT * C::A_TILE;
 #pragma unroll
@@ -204,7 +236,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             else
                                 ptx::tma_load_4d(dst, &map_a, full, cc * BKC, w0[i] + dj - p.PL, h0[i] + di - p.PT, n0[i]);
                         }
-                        ptx::tma_load_4d(sb + j * C::B_TILE, &map_b, full, 0, n_tile * BN, cc, tap);
+                        if (!armed) ptx::tma_load_4d(sb + j * C::B_TILE, &map_b, full, 0, n_tile * BN, cc, tap);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -288,15 +320,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (row == 0) {
-                    int *ctr = p.counters + (tile % tiles_mn);
+                    int *ctr = p.counters + 2 * (tile % tiles_mn);
                     atomicAdd(ctr, 1);
                     long long t0 = clock64();
-                    while (true) {                  // every sibling CTA is resident (cooperative launch): this terminates
+                    while (true) {                  // every sibling CTA is resident (grid <= SMs): this terminates
                         int seen;
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-                        if (seen >= p.split_target) break;
-                        __nanosleep(64);
+                        if (seen >= p.splits) break;
+                        __nanosleep(32);
                         if (clock64() - t0 > 4000000000LL) __trap();
+                    }
+                    // the last sibling to leave the wait resets the pair for the next launch
+                    if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
+                        ctr[1] = 0;
+                        __threadfence();
+                        ctr[0] = 0;
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -314,9 +352,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const float4 *src = reinterpret_cast<const float4 *>(p.workspace + ((size_t)m_tile * tile_rows + rr) * ldw +
                                                                           n_tile * BN) + c4;
                     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int sidx = 0; sidx < p.splits; ++sidx) {
-                        const float4 t4 = __ldcg(src + sidx * (slab / 4));
-                        sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
+                    // the loads of a group of slabs are issued together (one L2 round trip per group instead
+                    // of one per slab); the additions stay in slab order
+                    constexpr int G = 9;
+                    for (int s0 = 0; s0 < p.splits; s0 += G) {
+                        float4 t4[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            if (s0 + g < p.splits) t4[g] = __ldcg(src + (size_t)(s0 + g) * (slab / 4));
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            if (s0 + g < p.splits) { sum.x += t4[g].x; sum.y += t4[g].y; sum.z += t4[g].z; sum.w += t4[g].w; }
                     }
                     const int col = n_tile * BN + c4 * 4;
                     float v4[4] = {sum.x, sum.y, sum.z, sum.w};

@@ -126,6 +126,40 @@ cudaError_t set_smem_once(K kern, int bytes, bool (&done)[64]) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Launch with attributes.  t_pdl is set around a forward of a latency-mode network: kernels are then
+// launched with programmatic stream serialization, i.e. a kernel may start (prologue, weight prefetch)
+// while its predecessor drains; each of these kernels calls ptx::griddep_wait() before it touches memory
+// an earlier kernel of the stream writes.  Only kernels that contain that wait go through launch_ex.
+// `coop` (split-K: sibling CTAs wait for one another) asks for a cooperative launch; under PDL the
+// attribute is dropped -- the grid is at most one CTA per SM and a dependent kernel's CTAs are only
+// scheduled after every CTA of this grid has started, so the siblings are co-resident either way.
+thread_local bool t_pdl = false;
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool coop,
+                      Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    unsigned n = 0;
+    if (t_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    } else if (coop) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // tcgen05 kernel instantiations and their dispatch table
 typedef cudaError_t (*UmmaLauncher)(const CUtensorMap &, const CUtensorMap &, const umma_conv::Params &, int grid,
                                     cudaStream_t);
@@ -150,22 +184,8 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
-    if (grid < 0) {
-        // split-K: sibling CTAs wait for one another, so the whole grid must be resident: cooperative launch
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)-grid);
-        cfg.blockDim = dim3(umma_conv::kThreads);
-        cfg.dynamicSmemBytes = C::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
-    }
-    kern<<<grid, umma_conv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);
-    return cudaGetLastError();
+    // grid < 0 = split-K: sibling CTAs wait for one another, so the whole grid must be resident
+    return launch_ex(kern, (unsigned)(grid < 0 ? -grid : grid), umma_conv::kThreads, C::SMEM_BYTES, st, grid < 0, ma, mb, p);
 }
 
 #define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                              \
@@ -279,8 +299,7 @@ cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const r
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
-    kern<<<grid, rowpair::kThreads, C::SMEM_BYTES, st>>>(ma, mw, p, lin);
-    return cudaGetLastError();
+    return launch_ex(kern, (unsigned)grid, rowpair::kThreads, C::SMEM_BYTES, st, false, ma, mw, p, lin);
 }
 #define ROWPAIR_ENTRY(BF16, OBF, OC, SWZ, TR)                                                             \
     {BF16, OBF, OC, SWZ, TR, &launch_rowpair<BF16, OBF, OC, SWZ, TR, false>, &launch_rowpair<BF16, OBF, OC, SWZ, TR, true>, \
@@ -351,8 +370,7 @@ struct Block {
     void *d_wpack = nullptr;                    // [tap][OCp][IC] tf32-rounded fp32 or bf16
     float *d_scale = nullptr, *d_shift = nullptr;
     float *d_workspace = nullptr;               // split-K partial sums, one slab per K slice
-    int *d_counters = nullptr;                  // split-K arrival counters (monotonic)
-    int split_gen = 0;                          // launches so far: launch g waits for g * splits arrivals
+    int *d_counters = nullptr;                  // split-K arrival / departure counters per tile (zero between launches)
     void *d_conv_out = nullptr;                 // conv(+fused pool) output
     void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
     size_t conv_out_elems = 0, out_elems = 0;
@@ -400,6 +418,20 @@ struct dnnb_net {
     int prof_block = -1;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    // latency path (DNNB_LATENCY_MODE=1 at finalize): programmatic dependent launches, and the launch
+    // sequence of dnnb_net_forward_device replayed from a CUDA graph per (input, output) pointer pair
+    bool pdl = false, use_graph = false;
+    struct GraphSlot {
+        const void *in = nullptr;
+        void *out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long used = 0;
+    };
+    std::vector<GraphSlot> graphs;
+    unsigned long long graph_tick = 0;
+    int block_limit = 0;                // debug: forwards stop after this many blocks (0 = all)
+    const void *warm_in = nullptr;      // pointers of the last directly launched forward: the next forward on the
+    void *warm_out = nullptr;           // same pair is captured (function attributes and tensor maps are set by then)
 };
 
 namespace {
@@ -756,8 +788,7 @@ cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, smem, done);
     if (e != cudaSuccess) return e;
-    kern<<<grid, conv0::kThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_ex(kern, (unsigned)grid, conv0::kThreads, smem, st, false, p);
 }
 cudaError_t launch_conv0(const conv0::Params &p, bool bf16, bool out_bf16, int grid, cudaStream_t st, bool in_u8 = false) {
     if (in_u8) {
@@ -790,21 +821,18 @@ cudaError_t run_pool(const simt::PoolParams &p, bool bf16, int num_sms, cudaStre
     const size_t n = (size_t)p.B * p.OH * p.OW * p.C;
     if (p.C % 4 == 0 && p.KH == 2 && p.KW == 2 && p.SH == 1 && p.SW == 1 && p.PT == 0 && p.PL == 0 && p.OH == p.IH &&
         p.OW == p.IW && (long)p.B * p.OH < 2000000000L) {
-        const int threads = p.C / 4 < 256 ? (p.C / 4 + 31) / 32 * 32 : 256;
-        if (bf16) simt::maxpool_2x2s1_kernel<__nv_bfloat16><<<p.B * p.OH, threads, 0, st>>>(p);
-        else simt::maxpool_2x2s1_kernel<float><<<p.B * p.OH, threads, 0, st>>>(p);
-        return cudaGetLastError();
+        const unsigned threads = p.C / 4 < 256 ? (p.C / 4 + 31) / 32 * 32 : 256;
+        if (bf16) return launch_ex(simt::maxpool_2x2s1_kernel<__nv_bfloat16>, (unsigned)(p.B * p.OH), threads, 0, st, false, p);
+        return launch_ex(simt::maxpool_2x2s1_kernel<float>, (unsigned)(p.B * p.OH), threads, 0, st, false, p);
     }
     if (p.C % 4 == 0) {
-        const int grid = ew_grid(n / 4, num_sms);
-        if (bf16) simt::maxpool_vec4_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-        else simt::maxpool_vec4_kernel<float><<<grid, 256, 0, st>>>(p);
-        return cudaGetLastError();
+        const unsigned grid = ew_grid(n / 4, num_sms);
+        if (bf16) return launch_ex(simt::maxpool_vec4_kernel<__nv_bfloat16>, grid, 256u, 0, st, false, p);
+        return launch_ex(simt::maxpool_vec4_kernel<float>, grid, 256u, 0, st, false, p);
     }
-    const int grid = ew_grid(n, num_sms);
-    if (bf16) simt::maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-    else simt::maxpool_kernel<float><<<grid, 256, 0, st>>>(p);
-    return cudaGetLastError();
+    const unsigned grid = ew_grid(n, num_sms);
+    if (bf16) return launch_ex(simt::maxpool_kernel<__nv_bfloat16>, grid, 256u, 0, st, false, p);
+    return launch_ex(simt::maxpool_kernel<float>, grid, 256u, 0, st, false, p);
 }
 
 // launches the kernels of one block; `in` has the block's input storage type
@@ -842,13 +870,6 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         umma_conv::Params p = b.up;
         p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
         p.workspace = b.d_workspace; p.counters = b.d_counters;
-        if (p.splits > 1) {
-            if (b.split_gen >= (1 << 24)) {       // keep the monotonic counters far from overflow
-                CK(cudaMemsetAsync(b.d_counters, 0, (size_t)p.num_m_tiles * p.num_n_tiles * sizeof(int), st));
-                b.split_gen = 0;
-            }
-            p.split_target = ++b.split_gen * p.splits;
-        }
         if (b.pair) {
             pairconv::Params q = b.pp;
             q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out;
@@ -878,7 +899,14 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
 
 // in_u8: dev_in holds uint8 frames of the network's size and block 0 is the conv0 kernel, which then
 // normalises them in its own loader (no separate preprocessing kernel, 3 instead of 12 bytes per pixel read)
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(bool on) : prev(t_pdl) { t_pdl = on; }
+    ~PdlScope() { t_pdl = prev; }
+};
+
 int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st, bool in_u8 = false, int swap_rb = 0) {
+    PdlScope pdl(net->pdl);
     const void *cur = dev_in;
     Block &first = net->blocks.front();
     net->cur_in_u8 = in_u8;
@@ -894,7 +922,9 @@ int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t 
         CK(cudaGetLastError());
         cur = net->d_in_cast;
     }
-    for (size_t i = 0; i < net->blocks.size(); ++i) {
+    const size_t n_run = net->block_limit > 0 && (size_t)net->block_limit < net->blocks.size() ? (size_t)net->block_limit
+                                                                                               : net->blocks.size();
+    for (size_t i = 0; i < n_run; ++i) {
         Block &b = net->blocks[i];
         const bool last = i + 1 == net->blocks.size();
         void *override_out = (last && dev_out && !b.out_bf16) ? dev_out : nullptr;
@@ -914,6 +944,30 @@ int forward_impl(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t 
             net->prof_used++;
         }
         cur = override_out ? override_out : b.d_out;
+    }
+    return 0;
+}
+
+// Records one forward on `st` into a graph (stream capture; nothing executes).  Returns non-zero, with the
+// stream back in its normal state, when the capture cannot be made.
+int capture_forward(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream_t st, cudaGraphExec_t *exec) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    const int rc = forward_impl(net, dev_in, dev_out, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return 1;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
     }
     return 0;
 }
@@ -1108,6 +1162,8 @@ int dnnb_net_finalize(dnnb_net *net) {
     int h = net->H, w = net->W;
     bool in_bf16 = false;
     net->launches = 0;
+    net->pdl = latency_mode() && !getenv("DNNB_NO_PDL");
+    net->use_graph = latency_mode() && !getenv("DNNB_NO_GRAPH");
     for (size_t i = 0; i < net->blocks.size(); ++i) {
         Block &b = net->blocks[i];
         b.ih = h; b.iw = w;
@@ -1214,7 +1270,7 @@ int dnnb_net_finalize(dnnb_net *net) {
             }
             if (b.up.splits > 1) {
                 const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
-                const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * sizeof(int);
+                const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * 2 * sizeof(int);
                 CK(cudaMalloc(&b.d_workspace, ws));
                 CK(cudaMalloc(&b.d_counters, nc));
                 CK(cudaMemset(b.d_workspace, 0, ws));
@@ -1276,6 +1332,36 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
     net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
     net->last_in = dev_in;
+    if (net->use_graph && net->prof_block < 0) {
+        for (dnnb_net::GraphSlot &g : net->graphs)
+            if (g.in == dev_in && g.out == dev_out) {
+                g.used = ++net->graph_tick;
+                CK(cudaGraphLaunch(g.exec, st));
+                return 0;
+            }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (net->warm_in == dev_in && net->warm_out == dev_out && cudaStreamIsCapturing(st, &cs) == cudaSuccess &&
+            cs == cudaStreamCaptureStatusNone) {
+            cudaGraphExec_t exec = nullptr;
+            if (capture_forward(net, dev_in, dev_out, st, &exec) == 0) {
+                if (net->graphs.size() >= 4) {            // keep the four most recently used pointer pairs
+                    size_t victim = 0;
+                    for (size_t i = 1; i < net->graphs.size(); ++i)
+                        if (net->graphs[i].used < net->graphs[victim].used) victim = i;
+                    cudaGraphExecDestroy(net->graphs[victim].exec);
+                    net->graphs.erase(net->graphs.begin() + victim);
+                }
+                dnnb_net::GraphSlot g;
+                g.in = dev_in; g.out = dev_out; g.exec = exec; g.used = ++net->graph_tick;
+                net->graphs.push_back(g);
+                CK(cudaGraphLaunch(exec, st));
+                return 0;
+            }
+            net->use_graph = false;       // capture is not available here (legacy stream, driver): launch directly from now on
+        }
+        net->warm_in = dev_in;
+        net->warm_out = dev_out;
+    }
     return forward_impl(net, dev_in, dev_out, st);
 }
 
@@ -1703,6 +1789,18 @@ int dnnb_net_launches_per_forward(dnnb_net *net, int *n) {
     return 0;
 }
 
+int dnnb_net_debug_block_limit(dnnb_net *net, int blocks) {
+    if (check_net(net, true)) return 1;
+    DeviceGuard g(net->device);
+    CK(dnnb_sync_streams(net));
+    net->block_limit = blocks;
+    for (dnnb_net::GraphSlot &gs : net->graphs) cudaGraphExecDestroy(gs.exec);   // recorded for another limit
+    net->graphs.clear();
+    net->warm_in = nullptr;
+    net->warm_out = nullptr;
+    return 0;
+}
+
 int dnnb_net_destroy(dnnb_net *net) {
     if (!net) return 0;
     DeviceGuard g(net->device);
@@ -1718,6 +1816,7 @@ int dnnb_net_destroy(dnnb_net *net) {
         if (b.d_shift) cudaFree(b.d_shift);
     }
     for (auto &pr : net->prof_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (dnnb_net::GraphSlot &g : net->graphs) cudaGraphExecDestroy(g.exec);
     if (net->d_in2[0]) cudaFree(net->d_in2[0]);
     if (net->d_in2[1]) cudaFree(net->d_in2[1]);
     if (net->d_outf[1]) cudaFree(net->d_outf[1]);

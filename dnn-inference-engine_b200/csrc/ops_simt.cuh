@@ -152,6 +152,8 @@ struct PoolParams {
 // element, channel fastest.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolParams p) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();      // the input is the preceding kernel's output
     const size_t total = (size_t)p.B * p.OH * p.OW * p.C;
     const T *in = static_cast<const T *>(p.in);
     T *out = static_cast<T *>(p.out);
@@ -201,6 +203,8 @@ template <> struct Vec4<__nv_bfloat16> {
 
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_vec4_kernel(const PoolParams p) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();      // the input is the preceding kernel's output
     typedef typename Vec4<T>::raw Raw;
     const int c4 = p.C >> 2;
     const size_t total = (size_t)p.B * p.OH * p.OW * c4;
@@ -235,6 +239,8 @@ __global__ void __launch_bounds__(256) maxpool_vec4_kernel(const PoolParams p) {
 // x-1 and x, so every input element is loaded exactly twice (rows y and y+1) instead of four times.
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_2x2s1_kernel(const PoolParams p) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();      // the input is the preceding kernel's output
     typedef typename Vec4<T>::raw Raw;
     const int c4 = p.C >> 2;
     const int b = blockIdx.x / p.OH, oy = blockIdx.x - b * p.OH;

@@ -60,6 +60,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- TMA
+// Programmatic dependent launch (latency path, engine.cu `pdl`): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running.  griddep_launch lets the successor's CTAs be scheduled; griddep_wait blocks until the
+// predecessor has completed and its writes are visible -- everything before it may only touch memory no
+// kernel of the stream writes (weights, epilogue constants).  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }

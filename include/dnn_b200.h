@@ -160,6 +160,11 @@ int dnnb_net_profile_read(dnnb_net *net, float *total_ms, int *count);
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */
 int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
 
+/* Debug / measurement: forwards stop after the first `blocks` blocks (<= 0: all of them).  Timing
+ * forwards at increasing limits gives each block's in-situ share of the batch-1 latency, overlap
+ * between programmatically chained kernels included (tools/batch1_probe.py). */
+int dnnb_net_debug_block_limit(dnnb_net *net, int blocks);
+
 int dnnb_net_destroy(dnnb_net *net);
 
 /* ------------------------------------------------------------------------------------------

@@ -391,6 +391,45 @@ def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeyp
     assert normalised_error(out, gold) < TOL["tf32"]
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_latency_mode_graph_replay_equals_direct_launches(monkeypatch, precision):
+    """DNNB_LATENCY_MODE=1 also chains the kernels by programmatic dependent launch and replays the
+    device-resident forward (dnnb_net_forward_device) from a CUDA graph from the third call on the same
+    pointers.  Every replay must reproduce the directly launched result bit for bit -- the split-K
+    counters reset themselves on the device -- also after the input buffer's contents change, and the
+    graph-free, PDL-free launch sequence (DNNB_NO_GRAPH, DNNB_NO_PDL) must give the same bits."""
+    import torch
+    monkeypatch.setenv("DNNB_LATENCY_MODE", "1")
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    xs = [torch.from_numpy(make_images(1, seed=s)).to(dev) for s in (100, 101)]
+    x = torch.empty_like(xs[0])
+    y = torch.empty((1, 13, 13, 125), device=dev)
+
+    def run_all(calls):
+        eng = _yolo_engine(1, precision)
+        eng.kernel_plan()                       # builds the resident network
+        outs = []
+        with torch.cuda.stream(stream):
+            for i in range(calls):
+                x.copy_(xs[i % 2], non_blocking=True)
+                eng._net.forward_device(x.data_ptr(), y.data_ptr(), stream.cuda_stream)
+                stream.synchronize()
+                outs.append(y.cpu().numpy().copy())
+        eng.close()
+        return outs
+
+    outs = run_all(12)                          # calls 0-1 direct, call 1 captured, 2.. replayed
+    monkeypatch.setenv("DNNB_NO_GRAPH", "1")
+    monkeypatch.setenv("DNNB_NO_PDL", "1")
+    plain = run_all(2)
+    for i, o in enumerate(outs):
+        np.testing.assert_array_equal(o, plain[i % 2], err_msg="call %d" % i)
+    assert not np.array_equal(plain[0], plain[1])
+    gold = np.load(os.path.join(GOLDEN, "yolo_w0_i100.npz"))["out_openblas"]
+    assert normalised_error(outs[0], gold) < TOL[precision]
+
+
 def test_uint8_frames_match_numpy_preprocessing():
     """proj3/__init__.py:8-12 minus the resize.  The device-side /255 + BGR->RGB must be
     bit-identical to numpy's, so the network output equals the float32 path's exactly."""
