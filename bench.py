@@ -15,7 +15,9 @@ fused network.  One "step" = one pass of the hot path over the 4096 images.
   roofline: the dominant kernel (block 7, 3x3x1024->1024 on 13x13, 42% of the summed per-layer
            roofline), timed in situ with CUDA events around its launches inside the timed steps
   cpu_baseline: the reference's own OpenBLAS engine (oracle/_ref, compiled unmodified) timed on
-           this box's host cores on a bounded sample -- a reported baseline, not the target
+           this box's host cores on a bounded sample -- a reported baseline, not the target; its
+           AVX2+pthread engine alongside (cpu_baseline.avx_pthread)
+  batch1_latency: BASELINE configs[1], the device-resident batch-1 forward under the latency plan
 
   --impl reference : times that CPU reference alone (rank 0), same metric/unit/config.
 """
@@ -129,12 +131,15 @@ def openblas_threads():
         return os.cpu_count() or 1
 
 
-def cpu_reference_rate(n_images, weights, seed=100):
+def cpu_reference_rate(n_images, weights, seed=100, backend=None):
     """Times the reference CPU engine on n_images (batch 1 each, fresh graph per image, wall clock
-    around the run only, as proj3/__init__.py:24-26 does).  Returns (images/s, kind, cores, seconds)."""
+    around the run only, as proj3/__init__.py:24-26 does).  Returns (images/s, kind, cores, seconds).
+    backend: "ref_openblas" (default when built), "ref_avx" (proj3/dnn_avx.c, 4 pthreads), "oracle"."""
     import chain
     from synth import build_yolov2tiny, make_images
-    backend, kind = ("ref_openblas", "reference") if chain.available("ref_openblas") else ("oracle", "port")
+    if backend is None:
+        backend = "ref_openblas" if chain.available("ref_openblas") else "oracle"
+    kind = "port" if backend == "oracle" else "reference"
     if backend == "oracle":
         import build as oracle_build
         oracle_build.build_oracle()
@@ -146,8 +151,38 @@ def cpu_reference_rate(n_images, weights, seed=100):
         t0 = time.perf_counter()
         c.run(img)
         total += time.perf_counter() - t0
-    cores = openblas_threads() if backend == "ref_openblas" else (os.cpu_count() or 1)
+    cores = openblas_threads() if backend == "ref_openblas" else 4 if backend == "ref_avx" else 1
     return n_images / total, kind, cores, total
+
+
+def batch1_latency(_lib, spec, precision, device, forwards=100, warmup=10):
+    """BASELINE configs[1]: batch-1 latency of the device-resident forward under the latency plan
+    (DNNB_LATENCY_MODE=1: split-K over co-resident CTAs, kernels chained by programmatic dependent launch,
+    the launch sequence replayed from a CUDA graph).  Each forward is timed on its own with CUDA events."""
+    import torch
+    os.environ["DNNB_LATENCY_MODE"] = "1"
+    try:
+        net = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device)
+    finally:
+        os.environ.pop("DNNB_LATENCY_MODE", None)
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.current_stream(dev)
+    x = torch.rand((1, 416, 416, 3), device=dev)
+    y = torch.empty((1, 13, 13, 125), device=dev)
+    ts = []
+    for i in range(warmup + forwards):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        net.forward_device(x.data_ptr(), y.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        e1.synchronize()
+        if i >= warmup:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    launches = net.launches_per_forward()
+    net.close()
+    return {"median_us": round(statistics.median(ts), 1), "min_us": round(min(ts), 1), "forwards": forwards,
+            "launches_per_forward": launches, "precision": precision,
+            "plan": "DNNB_LATENCY_MODE=1: split-K, programmatic dependent launch chain, CUDA graph replay; input resident in HBM"}
 
 
 def dist_env():
@@ -403,12 +438,19 @@ def run_b200(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": "%d images, batch 1 each, %.1f s of CPU time; proj3 OpenBLAS engine compiled unmodified, "
                              "host has %d cpus" % (args.cpu_sample, secs, os.cpu_count() or 0)}
+            import chain
+            if chain.available("ref_avx"):      # the reference's second CPU engine (proj3/dnn_avx.c, P_THREADS 4)
+                rate2, _, cores2, secs2 = cpu_reference_rate(args.cpu_sample, weights, backend="ref_avx")
+                cpu["avx_pthread"] = {"value": rate2, "unit": UNIT, "cores": cores2, "kind": "reference",
+                                      "sample": "%d images, batch 1 each, %.1f s; proj3 AVX2+pthread engine compiled "
+                                                "unmodified" % (args.cpu_sample, secs2)}
+        b1 = batch1_latency(_lib, spec, args.precision, local_rank) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
             "e2e": e2e, "gpu_launches": net.launches_per_forward() * n_mb * args.steps,   # timed region of `value`
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "layers": layers,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "batch1_latency": b1, "layers": layers,
             "sum_layer_roofline_frac": (sum(max(algorithmic_bytes(i, mb, act_bytes) / (peaks["hbm_gbs"] * 1e9),
                                                  GFLOP_PER_IMAGE[i] * 1e9 * mb / (tensor_peak * 1e12)) for i in range(9))
                                         / (sum(l["ms"] for l in layers) * 1e-3)) if layers else None,
