@@ -345,47 +345,67 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int r0 = split * rows_per;
                 const int r1 = r0 + rows_per < tile_rows ? r0 + rows_per : tile_rows;
                 constexpr int C4 = BN / 4;
-                for (int u = row; u < (r1 - r0) * C4; u += 128) {
-                    const int rr = r0 + u / C4, c4 = u - (u / C4) * C4;
-                    const int m = m_tile * tile_rows + rr;                 // output pixel (im2col: linear index)
-                    if (m >= p.M_total) continue;
-                    const float4 *src = reinterpret_cast<const float4 *>(p.workspace + ((size_t)m_tile * tile_rows + rr) * ldw +
-                                                                          n_tile * BN) + c4;
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                    // the loads of a group of slabs are issued together (one L2 round trip per group instead
-                    // of one per slab); the additions stay in slab order
-                    constexpr int G = 9;
+                // Each thread finishes float4 units u = row, row + 128, ... of the share, U units per pass: the
+                // slab loads of a pass (U units x up to G slabs) are all issued before the first addition, so a
+                // pass costs one L2 round trip; the additions stay in slab order.
+                constexpr int G = 9, U = 2;
+                const int units = (r1 - r0) * C4;
+                for (int u0 = row; u0 < units; u0 += 128 * U) {
+                    const float4 *src[U];
+                    int m_of[U], col_of[U];
+                    bool ok[U];
+                    float4 sum[U];
+#pragma unroll
+                    for (int q = 0; q < U; ++q) {
+                        const int u = u0 + q * 128;
+                        const int rr = r0 + u / C4, c4 = u - (u / C4) * C4;
+                        m_of[q] = m_tile * tile_rows + rr;                 // output pixel (im2col: linear index)
+                        col_of[q] = n_tile * BN + c4 * 4;
+                        ok[q] = u < units && m_of[q] < p.M_total;
+                        src[q] = reinterpret_cast<const float4 *>(p.workspace + ((size_t)m_tile * tile_rows + rr) * ldw + n_tile * BN) + c4;
+                        sum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     for (int s0 = 0; s0 < p.splits; s0 += G) {
-                        float4 t4[G];
+                        float4 t4[U][G];
 #pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            if (s0 + g < p.splits) t4[g] = __ldcg(src + (size_t)(s0 + g) * (slab / 4));
+                        for (int q = 0; q < U; ++q)
 #pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            if (s0 + g < p.splits) { sum.x += t4[g].x; sum.y += t4[g].y; sum.z += t4[g].z; sum.w += t4[g].w; }
+                            for (int g = 0; g < G; ++g)
+                                if (ok[q] && s0 + g < p.splits) t4[q][g] = __ldcg(src[q] + (size_t)(s0 + g) * (slab / 4));
+#pragma unroll
+                        for (int q = 0; q < U; ++q)
+#pragma unroll
+                            for (int g = 0; g < G; ++g)
+                                if (ok[q] && s0 + g < p.splits) {
+                                    sum[q].x += t4[q][g].x; sum[q].y += t4[q][g].y; sum[q].z += t4[q][g].z; sum[q].w += t4[q][g].w;
+                                }
                     }
-                    const int col = n_tile * BN + c4 * 4;
-                    float v4[4] = {sum.x, sum.y, sum.z, sum.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
-                        if (p.leaky) y = fmaxf(y, 0.1f * y);
-                        if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
-                        else if (p.round_tf32) y = ptx::round_tf32(y);
-                        v4[e] = y;
-                    }
-                    if constexpr (OUT_BF16) {
-                        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+                    for (int q = 0; q < U; ++q) {
+                        if (!ok[q]) continue;
+                        const int m = m_of[q], col = col_of[q];
+                        float v4[4] = {sum[q].x, sum[q].y, sum[q].z, sum[q].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
-                    } else {
-                        float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
-                        if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                        else {
+                        for (int e = 0; e < 4; ++e) {
+                            float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
+                            if (p.leaky) y = fmaxf(y, 0.1f * y);
+                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                            else if (p.round_tf32) y = ptx::round_tf32(y);
+                            v4[e] = y;
+                        }
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (col + e < p.OC) o[e] = v4[e];
+                                if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
+                        } else {
+                            float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                            if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.OC) o[e] = v4[e];
+                            }
                         }
                     }
                 }

@@ -619,7 +619,9 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 fuse = tw >= 2 && th >= 2;
                 // a spatial tile spans nb images; with far fewer images in the batch it is mostly padding:
                 // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
-                if (fuse && net->B * 2 <= nb && latency_mode()) fuse = false;
+                // (DNNB_LAT_FUSE_NB: bring-up knob, keep the fused spatial tiles up to this many images per tile)
+                const int keep_nb = getenv("DNNB_LAT_FUSE_NB") ? atoi(getenv("DNNB_LAT_FUSE_NB")) : 0;
+                if (fuse && net->B * 2 <= nb && nb > keep_nb && latency_mode()) fuse = false;
             }
             UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
             const UmmaEntry *e = find_umma(key);
@@ -677,9 +679,14 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
                 const int kstages = total_kb / kbs;
                 p.splits = 1;
-                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && latency_mode()) {
+                // Splitting costs ~7 us (partials through L2, sibling wait, reduction) and a CTA streams one ring
+                // of smem stages per ~2 us round trip, so a K loop of up to three ring passes stays whole
+                // (measured, batch 1: block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
+                const bool long_k = kstages > 3 * e->stages || getenv("DNNB_SPLIT_MIN_STAGES");
+                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && long_k && latency_mode()) {
                     int sp = net->num_sms / tiles_mn;
-                    if (sp > kstages / 4) sp = kstages / 4;
+                    const int min_stages = getenv("DNNB_SPLIT_MIN_STAGES") ? atoi(getenv("DNNB_SPLIT_MIN_STAGES")) : 4;   // bring-up knob
+                    if (sp > kstages / min_stages) sp = kstages / min_stages;
                     if (sp >= 2) p.splits = sp;
                 }
                 const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
