@@ -118,6 +118,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t bar_empty = bar_full + 8 * STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * STAGES;
     const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_red = bar_tempty + 16;        // split-K: bulk copies of the sibling slabs into the idle smem ring
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -144,6 +145,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::mbar_init(bar_tfull + 8 * s, 1);
             ptx::mbar_init(bar_tempty + 8 * s, 128);
         }
+        ptx::mbar_init(bar_red, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
@@ -285,6 +287,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ------------------------------------------------------------------ epilogue
         const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
         const int row = quarter * 32 + lane;           // tile row = output pixel slot
+        uint32_t red_phase = 0;
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             const int acc = local % ACC;
@@ -317,6 +320,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(bar_tempty + 8 * acc);
+                asm volatile("fence.proxy.async;" ::: "memory");      // the siblings read the slabs with bulk copies (async proxy)
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (row == 0) {
@@ -339,73 +343,61 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 __threadfence();
-                // phase 2: rows [r0, r1) of the tile are this CTA's share: sum the slabs in order, finish, store
+                asm volatile("fence.proxy.async;" ::: "memory");
+                // phase 2: rows [r0, r1) of the tile are this CTA's share.  Their partial sums in every slab are
+                // pulled into the (now idle) smem ring by bulk copies, one per (slab, row), all in flight at once
+                // -- one L2 round trip instead of one per group of loads -- then summed IN SLAB ORDER, finished
+                // and stored.
                 const int tile_rows = MT * kBM;
                 const int rows_per = (tile_rows + p.splits - 1) / p.splits;
                 const int r0 = split * rows_per;
-                const int r1 = r0 + rows_per < tile_rows ? r0 + rows_per : tile_rows;
+                int r1 = r0 + rows_per < tile_rows ? r0 + rows_per : tile_rows;
+                if (m_tile * tile_rows + r1 > p.M_total) r1 = p.M_total - m_tile * tile_rows;     // rows past the last pixel
+                const int nrows = r1 - r0;
+                if (nrows <= 0) continue;
+                constexpr uint32_t ROW_BYTES = BN * 4;
+                if ((size_t)p.splits * nrows * ROW_BYTES > (size_t)STAGES * C::STAGE_BYTES) __trap();   // planner: MT = 1, splits <= 128
+                if (row == 0) ptx::mbar_expect_tx(bar_red, (uint32_t)(p.splits * nrows) * ROW_BYTES);
+                for (int c = row; c < p.splits * nrows; c += 128) {
+                    const int sidx = c / nrows, r = c - sidx * nrows;
+                    const float *src = p.workspace + sidx * slab + ((size_t)m_tile * tile_rows + r0 + r) * ldw + n_tile * BN;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_base + (uint32_t)c * ROW_BYTES), "l"(src), "r"(ROW_BYTES), "r"(bar_red) : "memory");
+                }
+                ptx::mbar_wait(bar_red, red_phase);
+                red_phase ^= 1;
                 constexpr int C4 = BN / 4;
-                // Each thread finishes float4 units u = row, row + 128, ... of the share, U units per pass: the
-                // slab loads of a pass (U units x up to G slabs) are all issued before the first addition, so a
-                // pass costs one L2 round trip; the additions stay in slab order.
-                constexpr int G = 9, U = 2;
-                const int units = (r1 - r0) * C4;
-                for (int u0 = row; u0 < units; u0 += 128 * U) {
-                    const float4 *src[U];
-                    int m_of[U], col_of[U];
-                    bool ok[U];
-                    float4 sum[U];
-#pragma unroll
-                    for (int q = 0; q < U; ++q) {
-                        const int u = u0 + q * 128;
-                        const int rr = r0 + u / C4, c4 = u - (u / C4) * C4;
-                        m_of[q] = m_tile * tile_rows + rr;                 // output pixel (im2col: linear index)
-                        col_of[q] = n_tile * BN + c4 * 4;
-                        ok[q] = u < units && m_of[q] < p.M_total;
-                        src[q] = reinterpret_cast<const float4 *>(p.workspace + ((size_t)m_tile * tile_rows + rr) * ldw + n_tile * BN) + c4;
-                        sum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 *red = reinterpret_cast<const float4 *>(smem);
+                for (int u = row; u < nrows * C4; u += 128) {
+                    const int r = u / C4, c4 = u - r * C4;
+                    const int m = m_tile * tile_rows + r0 + r;                 // output pixel (im2col: linear index)
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sidx = 0; sidx < p.splits; ++sidx) {
+                        const float4 t4 = red[(size_t)(sidx * nrows + r) * C4 + c4];
+                        sum.x += t4.x; sum.y += t4.y; sum.z += t4.z; sum.w += t4.w;
                     }
-                    for (int s0 = 0; s0 < p.splits; s0 += G) {
-                        float4 t4[U][G];
+                    const int col = n_tile * BN + c4 * 4;
+                    float v4[4] = {sum.x, sum.y, sum.z, sum.w};
 #pragma unroll
-                        for (int q = 0; q < U; ++q)
-#pragma unroll
-                            for (int g = 0; g < G; ++g)
-                                if (ok[q] && s0 + g < p.splits) t4[q][g] = __ldcg(src[q] + (size_t)(s0 + g) * (slab / 4));
-#pragma unroll
-                        for (int q = 0; q < U; ++q)
-#pragma unroll
-                            for (int g = 0; g < G; ++g)
-                                if (ok[q] && s0 + g < p.splits) {
-                                    sum[q].x += t4[q][g].x; sum[q].y += t4[q][g].y; sum[q].z += t4[q][g].z; sum[q].w += t4[q][g].w;
-                                }
+                    for (int e = 0; e < 4; ++e) {
+                        float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
+                        if (p.leaky) y = fmaxf(y, 0.1f * y);
+                        if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                        else if (p.round_tf32) y = ptx::round_tf32(y);
+                        v4[e] = y;
                     }
+                    if constexpr (OUT_BF16) {
+                        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
 #pragma unroll
-                    for (int q = 0; q < U; ++q) {
-                        if (!ok[q]) continue;
-                        const int m = m_of[q], col = col_of[q];
-                        float v4[4] = {sum[q].x, sum[q].y, sum[q].z, sum[q].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
-                            if (p.leaky) y = fmaxf(y, 0.1f * y);
-                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
-                            else if (p.round_tf32) y = ptx::round_tf32(y);
-                            v4[e] = y;
-                        }
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
+                    } else {
+                        float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                        if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                        else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
-                        } else {
-                            float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
-                            if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                            else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (col + e < p.OC) o[e] = v4[e];
-                            }
+                                if (col + e < p.OC) o[e] = v4[e];
                         }
                     }
                 }
