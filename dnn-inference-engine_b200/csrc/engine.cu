@@ -315,13 +315,68 @@ const RowpairEntry g_rowpair_table[] = {
     ROWPAIR_ENTRY(true, false, 32, 32, 4),  ROWPAIR_ENTRY(true, false, 32, 32, 2),
     ROWPAIR_ENTRY(true, false, 64, 64, 2),
 };
-const RowpairEntry *find_rowpair(bool bf16, bool out_bf16, int oc, int swz, int height) {
-    const char *cap = getenv("DNNB_ROWPAIR_MAX_TR");      // bring-up: cap the tile height
-    const int max_tr = cap ? atoi(cap) : 8;
+const RowpairEntry *find_rowpair(bool bf16, bool out_bf16, int oc, int swz, int height, int max_tr) {
     for (const RowpairEntry &e : g_rowpair_table)
         if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.oc == oc && e.swz == swz && height % e.tr == 0 && e.tr <= max_tr)
             return &e;
     return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// Planner switches from the environment, read once per dnnb_net_finalize (DESIGN.md section 4c lists
+// them).  Apart from DNNB_LATENCY_MODE they exist for bring-up, ablation measurements and tests that
+// force a particular kernel; the defaults are the measured best plan.
+struct Knobs {
+    bool latency = false;            // DNNB_LATENCY_MODE=1   small-batch plan: split-K, PDL chain, graph replay
+    bool no_pdl = false;             // DNNB_NO_PDL           latency plan without programmatic dependent launch
+    bool no_graph = false;           // DNNB_NO_GRAPH         latency plan without CUDA-graph replay
+    bool force_simt = false;         // DNNB_FORCE_SIMT       CUDA-core kernels everywhere
+    bool no_conv0 = false;           // DNNB_NO_CONV0         block 0 through the generic kernel (after a cast)
+    bool no_rowpair = false;         // DNNB_NO_ROWPAIR       blocks 1-2 through the generic kernel
+    int rowpair_linear = -1;         // DNNB_ROWPAIR_LINEAR=0|1 force / DNNB_NO_ROWPAIR_LINEAR: linearised tiles off
+    int rowpair_max_tr = 8;          // DNNB_ROWPAIR_MAX_TR   cap on the row-pair tile height
+    bool no_pool_first = false;      // DNNB_NO_POOL_FIRST    always activate before pooling
+    bool no_stage_out = false;       // DNNB_NO_STAGE_OUT     no smem staging of narrow odd output rows
+    bool no_mt2 = false;             // DNNB_NO_MT2           no 256-row CTA tiles
+    int mt2_mask = -1;               // DNNB_MT2_MASK         bit i: 256-row CTA tiles for block i
+    bool no_pair = false;            // DNNB_NO_PAIR          no CTA-pair kernel
+    int pair_mt = 1;                 // DNNB_PAIR_MT=2        512 x 256 pair tiles
+    int pair_min_tiles = -1;         // DNNB_PAIR_MIN_TILES   pair tiles needed to use the pair kernel (default: two waves)
+    bool pair_no_tail = false;       // DNNB_PAIR_NO_TAIL     pairs also run the partial last wave
+    bool no_pair_tail = false;       // DNNB_NO_PAIR_TAIL     rows past the full waves go to the single-CTA kernel only
+    bool no_tail = false;            // DNNB_NO_TAIL          no main/tail cut of wave-quantised 256 x 256 blocks
+    int lat_fuse_nb = 0;             // DNNB_LAT_FUSE_NB      latency plan: keep fused spatial tiles up to this many images
+    int split_min_stages = 0;        // DNNB_SPLIT_MIN_STAGES latency plan: K blocks per split (0: default 4, short loops whole)
+    bool no_u8_fusion = false;       // DNNB_NO_U8_FUSION     uint8 frames through a separate preprocessing kernel
+};
+
+Knobs read_knobs() {
+    auto flag = [](const char *name) { return getenv(name) != nullptr; };
+    auto num = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
+    Knobs k;
+    const char *lat = getenv("DNNB_LATENCY_MODE");
+    k.latency = lat && lat[0] == '1';
+    k.no_pdl = flag("DNNB_NO_PDL");
+    k.no_graph = flag("DNNB_NO_GRAPH");
+    k.force_simt = flag("DNNB_FORCE_SIMT");
+    k.no_conv0 = flag("DNNB_NO_CONV0");
+    k.no_rowpair = flag("DNNB_NO_ROWPAIR");
+    k.rowpair_linear = flag("DNNB_ROWPAIR_LINEAR") ? (num("DNNB_ROWPAIR_LINEAR", 0) != 0) : flag("DNNB_NO_ROWPAIR_LINEAR") ? 0 : -1;
+    k.rowpair_max_tr = num("DNNB_ROWPAIR_MAX_TR", 8);
+    k.no_pool_first = flag("DNNB_NO_POOL_FIRST");
+    k.no_stage_out = flag("DNNB_NO_STAGE_OUT");
+    k.no_mt2 = flag("DNNB_NO_MT2");
+    k.mt2_mask = num("DNNB_MT2_MASK", -1);
+    k.no_pair = flag("DNNB_NO_PAIR");
+    k.pair_mt = num("DNNB_PAIR_MT", 1) == 2 ? 2 : 1;
+    k.pair_min_tiles = num("DNNB_PAIR_MIN_TILES", -1);
+    k.pair_no_tail = flag("DNNB_PAIR_NO_TAIL");
+    k.no_pair_tail = flag("DNNB_NO_PAIR_TAIL");
+    k.no_tail = flag("DNNB_NO_TAIL");
+    k.lat_fuse_nb = num("DNNB_LAT_FUSE_NB", 0);
+    k.split_min_stages = num("DNNB_SPLIT_MIN_STAGES", 0);
+    k.no_u8_fusion = flag("DNNB_NO_U8_FUSION");
+    return k;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -420,6 +475,7 @@ struct dnnb_net {
     size_t prof_used = 0;
     // latency path (DNNB_LATENCY_MODE=1 at finalize): programmatic dependent launches, and the launch
     // sequence of dnnb_net_forward_device replayed from a CUDA graph per (input, output) pointer pair
+    Knobs knobs;
     bool pdl = false, use_graph = false;
     struct GraphSlot {
         const void *in = nullptr;
@@ -519,15 +575,6 @@ int encode_map_b(Block &b, CUtensorMap *map = nullptr, int bn_rows = 0) {
     return 0;
 }
 
-// DNNB_LATENCY_MODE=1 (read when a network is finalized) plans for small-batch latency: split-K over
-// co-resident CTAs (deterministic: partial sums are added in slice order) and im2col tiles instead of
-// mostly-padding spatial tiles.  Results are reproducible run to run but, because the K sum is cut
-// differently, not bit-identical to the default plan (fp32 reordering noise); default off.
-bool latency_mode() {
-    const char *v = getenv("DNNB_LATENCY_MODE");
-    return v && v[0] == '1';
-}
-
 // scale/shift + LeakyReLU + rounding is monotone non-decreasing when scale > 0: pooling may then
 // run on the raw accumulators (f(max(a, b)) == max(f(a), f(b)) exactly)
 bool all_scales_positive(const Block &b) {
@@ -546,10 +593,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     b.round_tf32 = net->precision == DNNB_TF32 && !last;
     b.family = DNNB_KERNEL_SIMT;
     b.pool_fused = false;
-    const bool force_simt = getenv("DNNB_FORCE_SIMT") != nullptr;
+    const Knobs &kn = net->knobs;
+    const bool force_simt = kn.force_simt;
 
     // first block straight from the raw 3-channel fp32 image: the patch-resident tcgen05 kernel
-    if (i == 0 && !in_bf16 && net->precision != DNNB_FP32 && !force_simt && !getenv("DNNB_NO_CONV0") && b.ic == 3 &&
+    if (i == 0 && !in_bf16 && net->precision != DNNB_FP32 && !force_simt && !kn.no_conv0 && b.ic == 3 &&
         b.oc == 16 && b.kh == 3 && b.kw == 3 && b.same && b.pool_k == 2 && b.pool_s == 2 &&
         b.ih % conv0::kTileRows == 0 && b.iw % 4 == 0) {
         b.family = DNNB_KERNEL_UMMA_CONV0;
@@ -562,18 +610,18 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         c.col_tiles = (b.iw + 127) / 128;
         c.num_tiles = net->B * (b.ih / conv0::kTileRows) * c.col_tiles;
         c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
-        c.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
+        c.pool_first = all_scales_positive(b) && !kn.no_pool_first;
         b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
         b.bn = 16; b.swz = 0;
         return;
     }
 
     // wide few-channel pooled blocks: patch-resident row-pair kernel
-    if (net->precision != DNNB_FP32 && !force_simt && !getenv("DNNB_NO_ROWPAIR") && b.same && b.kh == 3 && b.kw == 3 &&
+    if (net->precision != DNNB_FP32 && !force_simt && !kn.no_rowpair && b.same && b.kh == 3 && b.kw == 3 &&
         b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0) {
         const int row_bytes = b.ic * (in_bf16 ? 2 : 4);
         const RowpairEntry *e = (row_bytes == 32 || row_bytes == 64 || row_bytes == 128)
-                                    ? find_rowpair(in_bf16, b.out_bf16, b.oc, row_bytes, b.ih) : nullptr;
+                                    ? find_rowpair(in_bf16, b.out_bf16, b.oc, row_bytes, b.ih, kn.rowpair_max_tr) : nullptr;
         if (e) {
             b.family = DNNB_KERNEL_UMMA_ROWPAIR;
             b.rowpair = e;
@@ -588,11 +636,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
             // image widths that are a poor multiple of 128 columns (416/208/104: 19 % padding): tile the
             // linearised positions instead (W + 4 per row group, 2-4 % padding)
             const long lin_tiles = ((long)net->B * (b.ih / e->tr) * (b.iw + 4) + 127) / 128;
-            b.rp_linear = lin_tiles * 100 < (long)r.num_tiles * 95 && lin_tiles * 128 < (1L << 30) && !getenv("DNNB_NO_ROWPAIR_LINEAR");
-            if (getenv("DNNB_ROWPAIR_LINEAR")) b.rp_linear = atoi(getenv("DNNB_ROWPAIR_LINEAR")) != 0;
+            b.rp_linear = lin_tiles * 100 < (long)r.num_tiles * 95 && lin_tiles * 128 < (1L << 30);
+            if (kn.rowpair_linear >= 0) b.rp_linear = kn.rowpair_linear != 0;
             if (b.rp_linear) { r.num_tiles = (int)lin_tiles; r.col_tiles = 1; }
             r.leaky = b.leaky; r.round_tf32 = b.round_tf32;
-            r.pool_first = all_scales_positive(b) && !getenv("DNNB_NO_POOL_FIRST");
+            r.pool_first = all_scales_positive(b) && !kn.no_pool_first;
             b.grid = r.num_tiles < net->num_sms ? r.num_tiles : net->num_sms;
             return;
         }
@@ -619,20 +667,18 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 fuse = tw >= 2 && th >= 2;
                 // a spatial tile spans nb images; with far fewer images in the batch it is mostly padding:
                 // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
-                // (DNNB_LAT_FUSE_NB: bring-up knob, keep the fused spatial tiles up to this many images per tile)
-                const int keep_nb = getenv("DNNB_LAT_FUSE_NB") ? atoi(getenv("DNNB_LAT_FUSE_NB")) : 0;
-                if (fuse && net->B * 2 <= nb && nb > keep_nb && latency_mode()) fuse = false;
+                if (fuse && net->B * 2 <= nb && nb > kn.lat_fuse_nb && kn.latency) fuse = false;
             }
             UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
             const UmmaEntry *e = find_umma(key);
-            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !getenv("DNNB_NO_STAGE_OUT")) {
+            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out) {
                 UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
                 key_so.stage_out = true;
                 const UmmaEntry *e_so = find_umma(key_so);
                 if (e_so) e = e_so;
             }
             int mt = 1;
-            if (e && !getenv("DNNB_NO_MT2")) {
+            if (e && !kn.no_mt2) {
                 // 256-row CTA tiles (two M tiles share each weight tile) when there is enough work for
                 // at least two waves of them; DNNB_MT2_MASK (bit i = block i) overrides per block
                 const long m_rows = fuse ? (long)((net->B + nb - 1) / nb) * nb * b.ih * b.iw : (long)net->B * b.ih * b.iw;
@@ -644,7 +690,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // less L2->SMEM traffic is also less energy); a loss for blocks 4-5
                 const long k_total = (long)b.kh * b.kw * b.ic;
                 bool want = tiles2 >= 2L * net->num_sms && (2 * bn <= 256 || k_total >= 4096);
-                if (getenv("DNNB_MT2_MASK")) want = (atoi(getenv("DNNB_MT2_MASK")) >> i) & 1;
+                if (kn.mt2_mask >= 0) want = (kn.mt2_mask >> i) & 1;
                 UmmaKey key2 = key;
                 key2.mt = 2;
                 const UmmaEntry *e2 = want ? find_umma(key2) : nullptr;
@@ -682,10 +728,10 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // Splitting costs ~7 us (partials through L2, sibling wait, reduction) and a CTA streams one ring
                 // of smem stages per ~2 us round trip, so a K loop of up to three ring passes stays whole
                 // (measured, batch 1: block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
-                const bool long_k = kstages > 3 * e->stages || getenv("DNNB_SPLIT_MIN_STAGES");
-                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && long_k && latency_mode()) {
+                const bool long_k = kstages > 3 * e->stages || kn.split_min_stages > 0;
+                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && long_k && kn.latency) {
                     int sp = net->num_sms / tiles_mn;
-                    const int min_stages = getenv("DNNB_SPLIT_MIN_STAGES") ? atoi(getenv("DNNB_SPLIT_MIN_STAGES")) : 4;   // bring-up knob
+                    const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
                     if (sp > kstages / min_stages) sp = kstages / min_stages;
                     if (sp >= 2) p.splits = sp;
                 }
@@ -698,12 +744,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 b.umma_tail = nullptr;
                 const int sms = net->num_sms;
                 if (!fuse && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
-                    sms % 2 == 0 && !getenv("DNNB_NO_PAIR")) {
+                    sms % 2 == 0 && !kn.no_pair) {
                     // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
                     // MT = 2 everywhere 82.8 k, no pairs 82.5 k -- two accumulator stages and six smem stages are
                     // worth more than the last quarter of traffic
-                    int pmt = 1;
-                    if (getenv("DNNB_PAIR_MT")) pmt = atoi(getenv("DNNB_PAIR_MT")) == 2 ? 2 : 1;
+                    const int pmt = kn.pair_mt;
                     const PairEntry *pe = find_pair(in_bf16, b.out_bf16, pmt);
                     UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
                     const UmmaEntry *et = find_umma(kt);
@@ -711,11 +756,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                     const int rows_per = 2 * pmt * umma_conv::kBM;
                     const int m_all = p.M_total / rows_per;                 // whole pair tiles
                     const int tiles_p = m_all * p.num_n_tiles;
-                    const int min_tiles = getenv("DNNB_PAIR_MIN_TILES") ? atoi(getenv("DNNB_PAIR_MIN_TILES")) : 2 * pairs;
+                    const int min_tiles = kn.pair_min_tiles >= 0 ? kn.pair_min_tiles : 2 * pairs;
                     if (pe && et && tiles_p >= min_tiles && tiles_p > 0) {
                         // stop at the last full wave when the partial one would be less than half full
                         int main_m = m_all;
-                        if (tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs && !getenv("DNNB_PAIR_NO_TAIL")) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
+                        if (tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs && !kn.pair_no_tail) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
                         b.pair = pe;
                         pairconv::Params &q = b.pp;
                         q = pairconv::Params{};
@@ -733,7 +778,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         b.pair_tail = nullptr;
                         const PairEntry *pt = pmt == 1 ? find_pair(in_bf16, b.out_bf16, 1, 128) : nullptr;
                         const int m_pt = (p.M_total - rows_done) / (2 * umma_conv::kBM);
-                        if (pt && m_pt > 0 && !getenv("DNNB_NO_PAIR_TAIL")) {
+                        if (pt && m_pt > 0 && !kn.no_pair_tail) {
                             b.pair_tail = pt;
                             b.pp_tail = q;
                             b.pp_tail.m_base = rows_done;
@@ -763,7 +808,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // Measured: worth it for the 256 x 256 tiles (block 7: 1.98 -> 1.89 ms); 128 x 256 tiles cut any
                 // finer become L2-bandwidth bound and the tail costs as much as the wave it replaces.
                 if (!b.pair && !fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
-                    !getenv("DNNB_NO_TAIL")) {
+                    !kn.no_tail) {
                     const int main_m = (tiles / sms) * sms / p.num_n_tiles;           // whole m-tiles in the full waves
                     const int rows_left = p.M_total - main_m * mt * umma_conv::kBM;
                     const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
@@ -1169,8 +1214,9 @@ int dnnb_net_finalize(dnnb_net *net) {
     int h = net->H, w = net->W;
     bool in_bf16 = false;
     net->launches = 0;
-    net->pdl = latency_mode() && !getenv("DNNB_NO_PDL");
-    net->use_graph = latency_mode() && !getenv("DNNB_NO_GRAPH");
+    net->knobs = read_knobs();
+    net->pdl = net->knobs.latency && !net->knobs.no_pdl;
+    net->use_graph = net->knobs.latency && !net->knobs.no_graph;
     for (size_t i = 0; i < net->blocks.size(); ++i) {
         Block &b = net->blocks[i];
         b.ih = h; b.iw = w;
@@ -1444,9 +1490,8 @@ int ensure_u8(dnnb_net *net, int src_h = 0, int src_w = 0) {
 }
 // uint8 frames of the network's own size go straight into the conv0 kernel when it is block 0
 bool u8_fused(const dnnb_net *net, int src_h, int src_w) {
-    static const bool off = getenv("DNNB_NO_U8_FUSION") != nullptr;
     const bool same = (src_h <= 0 || src_h == net->H) && (src_w <= 0 || src_w == net->W);
-    return !off && same && net->blocks.front().family == DNNB_KERNEL_UMMA_CONV0 && net->W % 16 == 0;
+    return !net->knobs.no_u8_fusion && same && net->blocks.front().family == DNNB_KERNEL_UMMA_CONV0 && net->W % 16 == 0;
 }
 
 cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f32, int swap_rb, cudaStream_t st,
