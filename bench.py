@@ -179,9 +179,27 @@ def batch1_latency(_lib, spec, precision, device, forwards=100, warmup=10):
         if i >= warmup:
             ts.append(e0.elapsed_time(e1) * 1e3)
     launches = net.launches_per_forward()
+    # the same from pinned host buffers through the host-facing calls (H2D + forward + D2H + sync, wall clock)
+    hin = _lib.PinnedArray((1, 416, 416, 3))
+    hu8 = _lib.PinnedArray((1, 416, 416, 3), dtype=np.uint8)
+    hout = _lib.PinnedArray((1, 13, 13, 125))
+    hin.array[...] = x.cpu().numpy()
+    hu8.array[...] = np.random.default_rng(7).integers(0, 256, size=hu8.array.shape, dtype=np.uint8)
+    host = {}
+    for name, call in (("float32", lambda: net.forward(hin.array, hout.array)),
+                       ("uint8_frame", lambda: net.forward_u8(hu8.array, True, hout.array))):
+        tw = []
+        for i in range(warmup + forwards):
+            t0 = time.perf_counter()
+            call()
+            if i >= warmup:
+                tw.append((time.perf_counter() - t0) * 1e6)
+        host[name] = round(statistics.median(tw), 1)
+    hin.free(); hu8.free(); hout.free()
     net.close()
     return {"median_us": round(statistics.median(ts), 1), "min_us": round(min(ts), 1), "forwards": forwards,
             "launches_per_forward": launches, "precision": precision,
+            "e2e_host_median_us": host,   # pinned host image in -> head tensor back in host memory
             "plan": "DNNB_LATENCY_MODE=1: split-K, programmatic dependent launch chain, CUDA graph replay; input resident in HBM"}
 
 
