@@ -334,12 +334,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         __nanosleep(32);
                         if (clock64() - t0 > 4000000000LL) __trap();
                     }
-                    // the last sibling to leave the wait resets the pair for the next launch
-                    if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
-                        ctr[1] = 0;
-                        __threadfence();
-                        ctr[0] = 0;
-                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 __threadfence();
@@ -354,7 +348,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 int r1 = r0 + rows_per < tile_rows ? r0 + rows_per : tile_rows;
                 if (m_tile * tile_rows + r1 > p.M_total) r1 = p.M_total - m_tile * tile_rows;     // rows past the last pixel
                 const int nrows = r1 - r0;
-                if (nrows <= 0) continue;
+                // Departure (the atomic's round trip is kept off the critical path: issued after the copies below
+                // when there are any).  The last sibling to leave resets the pair for the next launch.
+                auto depart = [&]() {
+                    if (row == 0) {
+                        int *ctr = p.counters + 2 * (tile % tiles_mn);
+                        if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
+                            ctr[1] = 0;
+                            __threadfence();
+                            ctr[0] = 0;
+                        }
+                    }
+                };
+                if (nrows <= 0) { depart(); continue; }
                 constexpr uint32_t ROW_BYTES = BN * 4;
                 if ((size_t)p.splits * nrows * ROW_BYTES > (size_t)STAGES * C::STAGE_BYTES) __trap();   // planner: MT = 1, splits <= 128
                 if (row == 0) ptx::mbar_expect_tx(bar_red, (uint32_t)(p.splits * nrows) * ROW_BYTES);
@@ -364,6 +370,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(smem_base + (uint32_t)c * ROW_BYTES), "l"(src), "r"(ROW_BYTES), "r"(bar_red) : "memory");
                 }
+                depart();
                 ptx::mbar_wait(bar_red, red_phase);
                 red_phase ^= 1;
                 constexpr int C4 = BN / 4;
