@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdnn_b200.so")
 SOURCES = ["engine.cu"]
-DEPS = ["engine.cu", "conv0_umma.cuh", "conv_rowpair.cuh", "conv_umma.cuh", "ops_simt.cuh", "ptx.cuh", os.path.join("..", "..", "include", "dnn_b200.h")]
+# everything under csrc/ is compiled into the one translation unit
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [os.path.join("..", "..", "include", "dnn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
 

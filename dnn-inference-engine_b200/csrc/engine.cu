@@ -1,8 +1,11 @@
 // engine.cu -- libdnn_b200.so: the C ABI declared in include/dnn_b200.h.
 //   * op-level entry points with the reference's signatures (proj3/dnn_openblas.c)
-//   * the resident network: per-block kernel planning, weight prepack, TMA descriptors,
-//     HBM-resident activations, the forward launch sequence.
-// Host-side only; the kernels live in conv_umma.cuh (tcgen05/TMA) and ops_simt.cuh.
+//   * the resident network: weight prepack, HBM-resident activations, the forward launch sequence
+//     (direct, programmatically chained, or replayed from a CUDA graph), host-buffer pipelining,
+//     preprocessing and detection decoding around it.
+// Host-side only.  Planning lives in planner.cuh, the kernel dispatch tables in launchers.cuh, the
+// kernels in conv_umma.cuh / conv_pair.cuh / conv_rowpair.cuh / conv0_umma.cuh (tcgen05, TMA),
+// ops_simt.cuh and postproc.cuh.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -24,814 +27,11 @@
 #include "ops_simt.cuh"
 #include "postproc.cuh"
 
-namespace {
-
-thread_local std::string g_err;
-
-int fail(const char *fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_err = buf;
-    return 1;
-}
-
-#define CK(...)                                                                                       \
-    do {                                                                                              \
-        cudaError_t e_ = (__VA_ARGS__);                                                                    \
-        if (e_ != cudaSuccess)                                                                        \
-            return fail("%s:%d: %s -> %s", __FILE__, __LINE__, #__VA_ARGS__, cudaGetErrorString(e_));        \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------
-// driver entry points for tensor-map encoding (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
-                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode_tiled = nullptr;
-EncodeIm2colFn g_encode_im2col = nullptr;
-
-int load_driver_fns() {
-    if (g_encode_tiled && g_encode_im2col) return 0;
-    cudaDriverEntryPointQueryResult q;
-    void *f = nullptr;
-    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
-    if (!f || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available");
-    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f);
-    f = nullptr;
-    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q));
-    if (!f || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeIm2col not available");
-    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f);
-    return 0;
-}
-
-CUtensorMapSwizzle swizzle_enum(int swz) {
-    return swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-}
-
-// ------------------------------------------------------------------------------------------
-// host-side rounding used by the weight prepack (round to nearest even)
-float host_round_tf32(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return x;
-    u += 0xfffu + ((u >> 13) & 1u);
-    u &= 0xffffe000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-}
-uint16_t host_bf16(float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-
-int round_up(int a, int b) { return (a + b - 1) / b * b; }
-int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
-
-void out_pads(int in_size, int k, int s, int same, int *o, int *pf, int *pb) {
-    // TF SAME / VALID, proj3/dnn_openblas.py:127-142
-    if (same) {
-        *o = (in_size + s - 1) / s;
-        int pad = (*o - 1) * s + k - in_size;
-        if (pad < 0) pad = 0;
-        *pf = pad / 2;
-        *pb = pad - pad / 2;
-    } else {
-        *o = (in_size - k + 1 + s - 1) / s;
-        *pf = *pb = 0;
-    }
-}
-
-// opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel, device)
-template <typename K>
-cudaError_t set_smem_once(K kern, int bytes, bool (&done)[64]) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) done[dev] = true;
-    }
-    return cudaSuccess;
-}
-
-// ------------------------------------------------------------------------------------------
-// Launch with attributes.  t_pdl is set around a forward of a latency-mode network: kernels are then
-// launched with programmatic stream serialization, i.e. a kernel may start (prologue, weight prefetch)
-// while its predecessor drains; each of these kernels calls ptx::griddep_wait() before it touches memory
-// an earlier kernel of the stream writes.  Only kernels that contain that wait go through launch_ex.
-// `coop` (split-K: sibling CTAs wait for one another) asks for a cooperative launch; under PDL the
-// attribute is dropped -- the grid is at most one CTA per SM and a dependent kernel's CTAs are only
-// scheduled after every CTA of this grid has started, so the siblings are co-resident either way.
-thread_local bool t_pdl = false;
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool coop,
-                      Args &&...args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    unsigned n = 0;
-    if (t_pdl) {
-        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    } else if (coop) {
-        attr[n].id = cudaLaunchAttributeCooperative;
-        attr[n].val.cooperative = 1;
-        ++n;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n;
-    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
-
-// ------------------------------------------------------------------------------------------
-// tcgen05 kernel instantiations and their dispatch table
-typedef cudaError_t (*UmmaLauncher)(const CUtensorMap &, const CUtensorMap &, const umma_conv::Params &, int grid,
-                                    cudaStream_t);
-struct UmmaKey {
-    bool bf16, out_bf16;
-    int bn, swz, kbs;
-    bool im2col, pool;
-    int mt;   // 128-row M tiles per CTA tile
-    bool stage_out;   // output tile staged in smem (rows that are not 16-byte multiples)
-};
-struct UmmaEntry {
-    UmmaKey key;
-    UmmaLauncher launch;
-    int stages, smem;
-};
-
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false>
-cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
-                        cudaStream_t st) {
-    using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO>;
-    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO>;
-    static bool done[64] = {};
-    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
-    if (e != cudaSuccess) return e;
-    // grid < 0 = split-K: sibling CTAs wait for one another, so the whole grid must be resident
-    return launch_ex(kern, (unsigned)(grid < 0 ? -grid : grid), umma_conv::kThreads, C::SMEM_BYTES, st, grid < 0, ma, mb, p);
-}
-
-#define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                              \
-    {{BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT, false}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>,  \
-     umma_conv::Cfg<BN, SWZ, KBS, MT>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, MT>::SMEM_BYTES}
-#define UMMA_ENTRY_SO(BF16, BN, SWZ, KBS)                                                                  \
-    {{BF16, false, BN, SWZ, KBS, true, false, 1, true}, &launch_umma<BF16, false, BN, SWZ, KBS, true, false, 1, true>, \
-     umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES}
-#define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
-
-const UmmaEntry g_umma_table[] = {
-    // TF32 operands (fp32 storage in and out)
-    UMMA_ENTRY(false, false, 32, 64, 3, false, true),
-    UMMA_ENTRY(false, false, 64, 128, 1, false, true),
-    UMMA_ENTRY(false, false, 128, 128, 1, false, true),
-    UMMA_ENTRY(false, false, 256, 128, 1, false, true),
-    UMMA_ENTRY(false, false, 256, 128, 1, true, false),
-    UMMA_ENTRY(false, false, 128, 128, 1, true, false),
-    UMMA_ENTRY(false, false, 64, 128, 1, true, false),
-    UMMA_ENTRY(false, false, 32, 64, 3, true, false),
-    // BF16 operands, bf16 storage out
-    UMMA_ENTRY(true, true, 32, 32, 3, false, true),
-    UMMA_ENTRY(true, true, 64, 64, 3, false, true),
-    UMMA_ENTRY(true, true, 128, 128, 1, false, true),
-    UMMA_ENTRY(true, true, 256, 128, 1, false, true),
-    UMMA_ENTRY(true, true, 256, 128, 1, true, false),
-    UMMA_ENTRY(true, true, 128, 128, 1, true, false),
-    UMMA_ENTRY(true, true, 64, 64, 3, true, false),
-    UMMA_ENTRY(true, true, 32, 32, 3, true, false),
-    // BF16 operands, fp32 out (a network's last block)
-    UMMA_ENTRY(true, false, 32, 32, 3, false, true),
-    UMMA_ENTRY(true, false, 64, 64, 3, false, true),
-    UMMA_ENTRY(true, false, 128, 128, 1, false, true),
-    UMMA_ENTRY(true, false, 256, 128, 1, false, true),
-    UMMA_ENTRY(true, false, 256, 128, 1, true, false),
-    UMMA_ENTRY(true, false, 128, 128, 1, true, false),
-    UMMA_ENTRY(true, false, 64, 64, 3, true, false),
-    UMMA_ENTRY(true, false, 32, 32, 3, true, false),
-    // 256 x 256 CTA tiles (two M tiles share each weight tile) for the long-K 13x13 layers
-    UMMA_ENTRY_MT(false, false, 256, 128, 1, true, false, 2),
-    UMMA_ENTRY_MT(true, true, 256, 128, 1, true, false, 2),
-    UMMA_ENTRY_MT(true, false, 256, 128, 1, true, false, 2),
-    // the same for the fused-pool spatial tiles (two groups of nb images share each weight tile)
-    UMMA_ENTRY_MT(false, false, 128, 128, 1, false, true, 2),
-    UMMA_ENTRY_MT(false, false, 256, 128, 1, false, true, 2),
-    UMMA_ENTRY_MT(true, true, 128, 128, 1, false, true, 2),
-    UMMA_ENTRY_MT(true, true, 256, 128, 1, false, true, 2),
-    // output staged through smem: the 125-channel head (block 8)
-    UMMA_ENTRY_SO(false, 128, 128, 1),
-    UMMA_ENTRY_SO(true, 128, 128, 1),
-};
-
-const UmmaEntry *find_umma(const UmmaKey &k) {
-    for (const UmmaEntry &e : g_umma_table)
-        if (e.key.bf16 == k.bf16 && e.key.out_bf16 == k.out_bf16 && e.key.bn == k.bn && e.key.swz == k.swz &&
-            e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool && e.key.mt == k.mt &&
-            e.key.stage_out == k.stage_out)
-            return &e;
-    return nullptr;
-}
-
-// ------------------------------------------------------------------------------------------
-// CTA-pair kernel instantiations (conv_pair.cuh): tcgen05.mma.cta_group::2 for the long-K 13x13 blocks
-typedef cudaError_t (*PairLauncher)(const CUtensorMap &, const CUtensorMap &, const pairconv::Params &, int grid,
-                                    cudaStream_t);
-struct PairEntry {
-    bool bf16, out_bf16;
-    int mt, bn;
-    PairLauncher launch;
-    int stages;
-};
-template <bool BF16, bool OUT_BF16, int MT, int BN>
-cudaError_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const pairconv::Params &p, int grid, cudaStream_t st) {
-    using C = pairconv::Cfg<MT, BN>;
-    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT, BN>;
-    static bool done[64] = {};
-    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, pairconv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
-    return cudaGetLastError();
-}
-#define PAIR_ENTRY(BF16, OBF, MT, BN) {BF16, OBF, MT, BN, &launch_pair<BF16, OBF, MT, BN>, pairconv::Cfg<MT, BN>::STAGES}
-const PairEntry g_pair_table[] = {
-    PAIR_ENTRY(false, false, 1, 256), PAIR_ENTRY(false, false, 2, 256), PAIR_ENTRY(false, false, 1, 128),
-    PAIR_ENTRY(true, true, 1, 256),   PAIR_ENTRY(true, true, 2, 256),   PAIR_ENTRY(true, true, 1, 128),
-    PAIR_ENTRY(true, false, 1, 256),  PAIR_ENTRY(true, false, 2, 256),  PAIR_ENTRY(true, false, 1, 128),
-};
-const PairEntry *find_pair(bool bf16, bool out_bf16, int mt, int bn = 256) {
-    for (const PairEntry &e : g_pair_table)
-        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt && e.bn == bn) return &e;
-    return nullptr;
-}
-
-// ------------------------------------------------------------------------------------------
-// patch-resident row-pair kernel instantiations (conv_rowpair.cuh)
-typedef cudaError_t (*RowpairLauncher)(const CUtensorMap &, const CUtensorMap &, const rowpair::Params &,
-                                       const rowpair::LinMaps &, int grid, cudaStream_t);
-struct RowpairEntry {
-    bool bf16, out_bf16;
-    int oc, swz, tr;        // tr = output rows per tile
-    RowpairLauncher launch;         // 128-column tiles of the image
-    RowpairLauncher launch_linear;  // tiles over the linearised (row group, column) positions
-    int stages;
-};
-
-template <bool BF16, bool OUT_BF16, int OC, int SWZ, int TR, bool LINEAR>
-cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const rowpair::Params &p,
-                           const rowpair::LinMaps &lin, int grid, cudaStream_t st) {
-    using C = rowpair::Cfg<OC, SWZ, TR, LINEAR>;
-    auto kern = rowpair::conv_rowpair_kernel<BF16, OUT_BF16, OC, SWZ, TR, LINEAR>;
-    static bool done[64] = {};
-    cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
-    if (e != cudaSuccess) return e;
-    return launch_ex(kern, (unsigned)grid, rowpair::kThreads, C::SMEM_BYTES, st, false, ma, mw, p, lin);
-}
-#define ROWPAIR_ENTRY(BF16, OBF, OC, SWZ, TR)                                                             \
-    {BF16, OBF, OC, SWZ, TR, &launch_rowpair<BF16, OBF, OC, SWZ, TR, false>, &launch_rowpair<BF16, OBF, OC, SWZ, TR, true>, \
-     rowpair::Cfg<OC, SWZ, TR>::STAGES}
-// per shape in order of preference (measured on B200, batch 512): 4-row tiles win for 16->32 channels
-// (TF32 0.487 -> 0.468 ms, BF16 0.454 -> 0.396 ms; 8 rows leave too few patch stages), 2 rows for 32->64;
-// the planner takes the first entry whose TR divides the image height
-const RowpairEntry g_rowpair_table[] = {
-    ROWPAIR_ENTRY(false, false, 32, 64, 4), ROWPAIR_ENTRY(false, false, 32, 64, 2),
-    ROWPAIR_ENTRY(false, false, 64, 128, 2),
-    ROWPAIR_ENTRY(true, true, 32, 32, 4),   ROWPAIR_ENTRY(true, true, 32, 32, 2),
-    ROWPAIR_ENTRY(true, true, 64, 64, 2),
-    ROWPAIR_ENTRY(true, false, 32, 32, 4),  ROWPAIR_ENTRY(true, false, 32, 32, 2),
-    ROWPAIR_ENTRY(true, false, 64, 64, 2),
-};
-const RowpairEntry *find_rowpair(bool bf16, bool out_bf16, int oc, int swz, int height, int max_tr) {
-    for (const RowpairEntry &e : g_rowpair_table)
-        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.oc == oc && e.swz == swz && height % e.tr == 0 && e.tr <= max_tr)
-            return &e;
-    return nullptr;
-}
-
-// ------------------------------------------------------------------------------------------
-// Planner switches from the environment, read once per dnnb_net_finalize (DESIGN.md section 4c lists
-// them).  Apart from DNNB_LATENCY_MODE they exist for bring-up, ablation measurements and tests that
-// force a particular kernel; the defaults are the measured best plan.
-struct Knobs {
-    bool latency = false;            // DNNB_LATENCY_MODE=1   small-batch plan: split-K, PDL chain, graph replay
-    bool no_pdl = false;             // DNNB_NO_PDL           latency plan without programmatic dependent launch
-    bool no_graph = false;           // DNNB_NO_GRAPH         latency plan without CUDA-graph replay
-    bool force_simt = false;         // DNNB_FORCE_SIMT       CUDA-core kernels everywhere
-    bool no_conv0 = false;           // DNNB_NO_CONV0         block 0 through the generic kernel (after a cast)
-    bool no_rowpair = false;         // DNNB_NO_ROWPAIR       blocks 1-2 through the generic kernel
-    int rowpair_linear = -1;         // DNNB_ROWPAIR_LINEAR=0|1 force / DNNB_NO_ROWPAIR_LINEAR: linearised tiles off
-    int rowpair_max_tr = 8;          // DNNB_ROWPAIR_MAX_TR   cap on the row-pair tile height
-    bool no_pool_first = false;      // DNNB_NO_POOL_FIRST    always activate before pooling
-    bool no_stage_out = false;       // DNNB_NO_STAGE_OUT     no smem staging of narrow odd output rows
-    bool no_mt2 = false;             // DNNB_NO_MT2           no 256-row CTA tiles
-    int mt2_mask = -1;               // DNNB_MT2_MASK         bit i: 256-row CTA tiles for block i
-    bool no_pair = false;            // DNNB_NO_PAIR          no CTA-pair kernel
-    int pair_mt = 1;                 // DNNB_PAIR_MT=2        512 x 256 pair tiles
-    int pair_min_tiles = -1;         // DNNB_PAIR_MIN_TILES   pair tiles needed to use the pair kernel (default: two waves)
-    bool pair_no_tail = false;       // DNNB_PAIR_NO_TAIL     pairs also run the partial last wave
-    bool no_pair_tail = false;       // DNNB_NO_PAIR_TAIL     rows past the full waves go to the single-CTA kernel only
-    bool no_tail = false;            // DNNB_NO_TAIL          no main/tail cut of wave-quantised 256 x 256 blocks
-    int lat_fuse_nb = 0;             // DNNB_LAT_FUSE_NB      latency plan: keep fused spatial tiles up to this many images
-    int split_min_stages = 0;        // DNNB_SPLIT_MIN_STAGES latency plan: K blocks per split (0: default 4, short loops whole)
-    bool no_u8_fusion = false;       // DNNB_NO_U8_FUSION     uint8 frames through a separate preprocessing kernel
-};
-
-Knobs read_knobs() {
-    auto flag = [](const char *name) { return getenv(name) != nullptr; };
-    auto num = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
-    Knobs k;
-    const char *lat = getenv("DNNB_LATENCY_MODE");
-    k.latency = lat && lat[0] == '1';
-    k.no_pdl = flag("DNNB_NO_PDL");
-    k.no_graph = flag("DNNB_NO_GRAPH");
-    k.force_simt = flag("DNNB_FORCE_SIMT");
-    k.no_conv0 = flag("DNNB_NO_CONV0");
-    k.no_rowpair = flag("DNNB_NO_ROWPAIR");
-    k.rowpair_linear = flag("DNNB_ROWPAIR_LINEAR") ? (num("DNNB_ROWPAIR_LINEAR", 0) != 0) : flag("DNNB_NO_ROWPAIR_LINEAR") ? 0 : -1;
-    k.rowpair_max_tr = num("DNNB_ROWPAIR_MAX_TR", 8);
-    k.no_pool_first = flag("DNNB_NO_POOL_FIRST");
-    k.no_stage_out = flag("DNNB_NO_STAGE_OUT");
-    k.no_mt2 = flag("DNNB_NO_MT2");
-    k.mt2_mask = num("DNNB_MT2_MASK", -1);
-    k.no_pair = flag("DNNB_NO_PAIR");
-    k.pair_mt = num("DNNB_PAIR_MT", 1) == 2 ? 2 : 1;
-    k.pair_min_tiles = num("DNNB_PAIR_MIN_TILES", -1);
-    k.pair_no_tail = flag("DNNB_PAIR_NO_TAIL");
-    k.no_pair_tail = flag("DNNB_NO_PAIR_TAIL");
-    k.no_tail = flag("DNNB_NO_TAIL");
-    k.lat_fuse_nb = num("DNNB_LAT_FUSE_NB", 0);
-    k.split_min_stages = num("DNNB_SPLIT_MIN_STAGES", 0);
-    k.no_u8_fusion = flag("DNNB_NO_U8_FUSION");
-    return k;
-}
-
-// ------------------------------------------------------------------------------------------
-struct Block {
-    // description
-    int kh = 0, kw = 0, ic = 0, oc = 0, same = 1;
-    bool has_bn = false, leaky = false;
-    int pool_k = 0, pool_s = 0, pool_same = 1;
-    std::vector<float> kernel, scale, shift;   // HWIO fp32; folded epilogue constants [oc]
-    // geometry
-    int ih = 0, iw = 0;                         // input spatial
-    int ch = 0, cw = 0, pt = 0, pl = 0;         // conv output spatial, top/left pad
-    int oh = 0, ow = 0, ppt = 0, ppl = 0;       // block output spatial (after pool), pool pads
-    // plan
-    int family = DNNB_KERNEL_SIMT;
-    bool pool_fused = false, pool_separate = false;
-    bool in_bf16 = false, out_bf16 = false;     // storage types
-    bool round_tf32 = false;
-    const UmmaEntry *umma = nullptr;
-    bool op_bf16 = false;                       // conv0: MMA operand type (its input is always fp32)
-    conv0::Params c0{};
-    const RowpairEntry *rowpair = nullptr;
-    rowpair::Params rp{};
-    umma_conv::Params up{};
-    CUtensorMap map_a{}, map_b{};
-    // tail launch (im2col blocks whose tile count is not a whole number of waves): the rows left after
-    // the last full wave, in finer tiles (smaller BN, MT = 1) so that they spread over all SMs
-    bool rp_linear = false;              // row-pair kernel: tiles over linearised positions (conv_rowpair.cuh LINEAR)
-    rowpair::LinMaps lin_maps{};
-    const PairEntry *pair = nullptr;     // main launch on CTA pairs (cta_group::2) instead of b.umma
-    pairconv::Params pp{};
-    CUtensorMap map_b_pair{};            // weights map with a 128-row box: each CTA of a pair loads half a B tile
-    // the last whole pair tiles of a block, past the full waves: pairs again, but 256 x 128 tiles (64-row B halves)
-    const PairEntry *pair_tail = nullptr;
-    pairconv::Params pp_tail{};
-    CUtensorMap map_b_pair_tail{};
-    int grid_pair_tail = 0;
-    const UmmaEntry *umma_tail = nullptr;
-    CUtensorMap map_b_tail{};
-    umma_conv::Params up_tail{};
-    int grid_tail = 0;
-    const void *map_a_base = nullptr;           // input pointer the A map was encoded for
-    int bn = 0, swz = 0, grid = 0;
-    // device memory
-    float *d_kernel = nullptr;                  // HWIO fp32 (SIMT)
-    void *d_wpack = nullptr;                    // [tap][OCp][IC] tf32-rounded fp32 or bf16
-    float *d_scale = nullptr, *d_shift = nullptr;
-    float *d_workspace = nullptr;               // split-K partial sums, one slab per K slice
-    int *d_counters = nullptr;                  // split-K arrival / departure counters per tile (zero between launches)
-    void *d_conv_out = nullptr;                 // conv(+fused pool) output
-    void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
-    size_t conv_out_elems = 0, out_elems = 0;
-};
-
-}  // namespace
-
-struct dnnb_net {
-    int device = 0, precision = DNNB_TF32;
-    int B = 0, H = 0, W = 0, C = 0;
-    std::vector<Block> blocks;
-    bool finalized = false;
-    cudaStream_t stream = nullptr;
-    float *d_in = nullptr;        // fp32 staging of the host input (= d_in2[0])
-    // host path pipelining: H2D of forward i+1 and D2H of forward i-1 overlap the kernels of forward i
-    float *d_in2[2] = {nullptr, nullptr};
-    float *d_outf[2] = {nullptr, nullptr};   // final fp32 outputs, alternating (d_outf[0] is the last block's own buffer)
-    const float *last_final = nullptr;       // where the most recent forward left its result
-    const void *last_in = nullptr;           // fp32 device input of the most recent forward
-    // uint8 frames (proj3/__init__.py:8-12 without the resize): staging + the /255 table
-    uint8_t *d_u8[2] = {nullptr, nullptr};
-    size_t u8_capacity = 0;       // bytes per staging buffer
-    float *d_lut = nullptr;
-    uint32_t *d_lut_conv0 = nullptr;   // the same table as finished block-0 operand bits (conv0_umma.cuh IN_U8)
-    bool cur_in_u8 = false;            // set by forward_impl for the block-0 launch
-    int cur_swap_rb = 0;
-    // cv2-exact bilinear resize of frames that are not in_h x in_w: per-axis offset / weight tables
-    int *d_resize_tab = nullptr;  // [xofs W][xw W][yofs H][yw H]
-    int resize_sh = 0, resize_sw = 0;
-    // on-device detection decoding (postproc.cuh): label boxes + counts, double-buffered like the outputs
-    void *d_dets[2] = {nullptr, nullptr};
-    int *d_counts[2] = {nullptr, nullptr};
-    float score_thr = 0.3f;      // proj3/yolov2tiny.py:156
-    double iou_thr = 0.3;        // :164
-    int max_det = 32;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
-    int flip = 0;
-    void *d_in_cast = nullptr;    // input in the first tcgen05 block's storage type
-    void *d_flush = nullptr;      // L2 flush scratch for dnnb_net_time_blocks
-    int num_sms = 148;
-    int launches = 0;
-    // optional in-situ timing of one block (bench.py's roofline leg): event pairs recorded
-    // around that block's kernels on whatever stream the forward runs on
-    int prof_block = -1;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
-    size_t prof_used = 0;
-    // latency path (DNNB_LATENCY_MODE=1 at finalize): programmatic dependent launches, and the launch
-    // sequence of dnnb_net_forward_device replayed from a CUDA graph per (input, output) pointer pair
-    Knobs knobs;
-    bool pdl = false, use_graph = false;
-    struct GraphSlot {
-        const void *in = nullptr;
-        void *out = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        unsigned long long used = 0;
-    };
-    std::vector<GraphSlot> graphs;
-    unsigned long long graph_tick = 0;
-    int block_limit = 0;                // debug: forwards stop after this many blocks (0 = all)
-    const void *warm_in = nullptr;      // pointers of the last directly launched forward: the next forward on the
-    void *warm_out = nullptr;           // same pair is captured (function attributes and tensor maps are set by then)
-};
+#include "host_util.cuh"
+#include "launchers.cuh"
+#include "planner.cuh"
 
 namespace {
-
-struct DeviceGuard {
-    int prev = 0;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() { cudaSetDevice(prev); }
-};
-
-int encode_map_a(dnnb_net *net, Block &b, const void *in_ptr) {
-    const int es = b.in_bf16 ? 2 : 4;
-    const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    cuuint64_t dims[4] = {(cuuint64_t)b.ic, (cuuint64_t)b.iw, (cuuint64_t)b.ih, (cuuint64_t)net->B};
-    cuuint64_t strides[3] = {(cuuint64_t)b.ic * es, (cuuint64_t)b.iw * b.ic * es, (cuuint64_t)b.ih * b.iw * b.ic * es};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    const int bkc = b.swz / es;
-    CUresult r;
-    if (b.family == DNNB_KERNEL_UMMA_IM2COL) {
-        int lower[2] = {-b.pl, -b.pt};
-        int upper[2] = {(b.kw - 1 - b.pl) - (b.kw - 1), (b.kh - 1 - b.pt) - (b.kh - 1)};   // pad_back - (k-1)
-        r = g_encode_im2col(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper, (cuuint32_t)bkc,
-                            (cuuint32_t)umma_conv::kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz),
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR && b.rp_linear) {
-        // one im2col map per patch plane s: base pixels w in [-3, W], h in {s-1, s-1+TR, ...} (H/TR of them),
-        // walked W-fastest, 130 positions per load (conv_rowpair.cuh, LINEAR)
-        const int tr = b.rowpair->tr;
-        cuuint32_t estr_lin[4] = {1, 1, (cuuint32_t)tr, 1};
-        r = CUDA_SUCCESS;
-        for (int s = 0; s < tr + 2 && r == CUDA_SUCCESS; ++s) {
-            int lower[2] = {-3, s - 1};
-            int upper[2] = {1, s - tr};
-            r = g_encode_im2col(&b.lin_maps.m[s], dt, 4, const_cast<void *>(in_ptr), dims, strides, lower, upper,
-                                (cuuint32_t)b.ic, (cuuint32_t)rowpair::kPatchW, estr_lin, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        }
-    } else if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
-        cuuint32_t box[4] = {(cuuint32_t)b.ic, (cuuint32_t)rowpair::kPatchW, (cuuint32_t)(b.rowpair->tr + 2), 1};
-        r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else {
-        cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)b.up.tw, (cuuint32_t)b.up.th, (cuuint32_t)b.up.nb};
-        r = g_encode_tiled(&b.map_a, dt, 4, const_cast<void *>(in_ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
-    if (r != CUDA_SUCCESS) return fail("tensor-map encode (A, family %d) failed: CUresult %d", b.family, (int)r);
-    b.map_a_base = in_ptr;
-    return 0;
-}
-
-int encode_map_b(Block &b, CUtensorMap *map = nullptr, int bn_rows = 0) {
-    if (!map) map = &b.map_b;
-    if (!bn_rows) bn_rows = b.bn;
-    const int es = b.in_bf16 ? 2 : 4;
-    const CUtensorMapDataType dt = b.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    if (b.family == DNNB_KERNEL_UMMA_ROWPAIR) {
-        cuuint64_t dims[3] = {(cuuint64_t)b.ic, (cuuint64_t)(3 * b.oc), 3};
-        cuuint64_t strides[2] = {(cuuint64_t)b.ic * es, (cuuint64_t)3 * b.oc * b.ic * es};
-        cuuint32_t box[3] = {(cuuint32_t)b.ic, (cuuint32_t)(3 * b.oc), 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = g_encode_tiled(&b.map_b, dt, 3, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail("tensor-map encode (row-pair weights) failed: CUresult %d", (int)r);
-        return 0;
-    }
-    // [tap][channel chunk][OCp][BKC]: the B tile of a K block (BN rows x one swizzle span) is one
-    // contiguous BN*SWZ-byte run, so cold weights stream from HBM instead of being gathered line by line
-    const int ocp = b.up.num_n_tiles * b.bn;
-    const int bkc = b.swz / es;
-    cuuint64_t dims[4] = {(cuuint64_t)bkc, (cuuint64_t)ocp, (cuuint64_t)(b.ic / bkc), (cuuint64_t)(b.kh * b.kw)};
-    cuuint64_t strides[3] = {(cuuint64_t)b.swz, (cuuint64_t)ocp * b.swz, (cuuint64_t)(b.ic / bkc) * ocp * b.swz};
-    cuuint32_t box[4] = {(cuuint32_t)bkc, (cuuint32_t)bn_rows, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode_tiled(map, dt, 4, b.d_wpack, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                swizzle_enum(b.swz), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("tensor-map encode (weights) failed: CUresult %d", (int)r);
-    return 0;
-}
-
-// scale/shift + LeakyReLU + rounding is monotone non-decreasing when scale > 0: pooling may then
-// run on the raw accumulators (f(max(a, b)) == max(f(a), f(b)) exactly)
-bool all_scales_positive(const Block &b) {
-    for (float v : b.scale)
-        if (!(v > 0.f)) return false;
-    return true;
-}
-
-// Decide how block `i` runs.  in_bf16: storage type of its input.
-void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
-    Block &b = net->blocks[i];
-    const bool last = i + 1 == net->blocks.size();
-    const bool want_bf16 = net->precision == DNNB_BF16;
-    b.in_bf16 = in_bf16;
-    b.out_bf16 = want_bf16 && !last;
-    b.round_tf32 = net->precision == DNNB_TF32 && !last;
-    b.family = DNNB_KERNEL_SIMT;
-    b.pool_fused = false;
-    const Knobs &kn = net->knobs;
-    const bool force_simt = kn.force_simt;
-
-    // first block straight from the raw 3-channel fp32 image: the patch-resident tcgen05 kernel
-    if (i == 0 && !in_bf16 && net->precision != DNNB_FP32 && !force_simt && !kn.no_conv0 && b.ic == 3 &&
-        b.oc == 16 && b.kh == 3 && b.kw == 3 && b.same && b.pool_k == 2 && b.pool_s == 2 &&
-        b.ih % conv0::kTileRows == 0 && b.iw % 4 == 0) {
-        b.family = DNNB_KERNEL_UMMA_CONV0;
-        b.pool_fused = true;
-        b.pool_separate = false;
-        b.op_bf16 = want_bf16;
-        conv0::Params &c = b.c0;
-        c = conv0::Params{};
-        c.B = net->B; c.H = b.ih; c.W = b.iw;
-        c.col_tiles = (b.iw + 127) / 128;
-        c.num_tiles = net->B * (b.ih / conv0::kTileRows) * c.col_tiles;
-        c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
-        c.pool_first = all_scales_positive(b) && !kn.no_pool_first;
-        b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;
-        b.bn = 16; b.swz = 0;
-        return;
-    }
-
-    // wide few-channel pooled blocks: patch-resident row-pair kernel
-    if (net->precision != DNNB_FP32 && !force_simt && !kn.no_rowpair && b.same && b.kh == 3 && b.kw == 3 &&
-        b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0) {
-        const int row_bytes = b.ic * (in_bf16 ? 2 : 4);
-        const RowpairEntry *e = (row_bytes == 32 || row_bytes == 64 || row_bytes == 128)
-                                    ? find_rowpair(in_bf16, b.out_bf16, b.oc, row_bytes, b.ih, kn.rowpair_max_tr) : nullptr;
-        if (e) {
-            b.family = DNNB_KERNEL_UMMA_ROWPAIR;
-            b.rowpair = e;
-            b.pool_fused = true;
-            b.pool_separate = false;
-            b.bn = b.oc; b.swz = row_bytes;
-            rowpair::Params &r = b.rp;
-            r = rowpair::Params{};
-            r.B = net->B; r.H = b.ih; r.W = b.iw;
-            r.col_tiles = (b.iw + 127) / 128;
-            r.num_tiles = net->B * (b.ih / e->tr) * r.col_tiles;
-            // image widths that are a poor multiple of 128 columns (416/208/104: 19 % padding): tile the
-            // linearised positions instead (W + 4 per row group, 2-4 % padding)
-            const long lin_tiles = ((long)net->B * (b.ih / e->tr) * (b.iw + 4) + 127) / 128;
-            b.rp_linear = lin_tiles * 100 < (long)r.num_tiles * 95 && lin_tiles * 128 < (1L << 30);
-            if (kn.rowpair_linear >= 0) b.rp_linear = kn.rowpair_linear != 0;
-            if (b.rp_linear) { r.num_tiles = (int)lin_tiles; r.col_tiles = 1; }
-            r.leaky = b.leaky; r.round_tf32 = b.round_tf32;
-            r.pool_first = all_scales_positive(b) && !kn.no_pool_first;
-            b.grid = r.num_tiles < net->num_sms ? r.num_tiles : net->num_sms;
-            return;
-        }
-    }
-
-    if (net->precision != DNNB_FP32 && !force_simt && b.same && b.ch == b.ih && b.cw == b.iw) {
-        const int es = in_bf16 ? 2 : 4;
-        const int row_bytes = b.ic * es;
-        const int swz = row_bytes >= 128 ? 128 : row_bytes;
-        const bool k_ok = (row_bytes == 32 || row_bytes == 64 || row_bytes % 128 == 0);
-        const int bn = b.oc <= 32 ? 32 : b.oc <= 64 ? 64 : b.oc <= 128 ? 128 : 256;
-        const int ocp = round_up(b.oc, bn);
-        const int c_chunks = row_bytes / swz;
-        const int total_kb = b.kh * b.kw * c_chunks;
-        const int kbs = (swz < 128 && total_kb % 3 == 0) ? 3 : 1;
-        if (k_ok && ocp <= 1024) {
-            // fused pool geometry: tile = nb x th x tw, powers of two, product 128, tw <= 16, th >= 2
-            bool fuse = b.pool_k == 2 && b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0 && b.oc % 8 == 0;
-            int tw = 1, th = 1, nb = 1;
-            if (fuse) {
-                while (tw < 16 && b.iw % (tw * 2) == 0) tw *= 2;
-                while (tw * th < 128 && b.ih % (th * 2) == 0) th *= 2;
-                nb = 128 / (tw * th);
-                fuse = tw >= 2 && th >= 2;
-                // a spatial tile spans nb images; with far fewer images in the batch it is mostly padding:
-                // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
-                if (fuse && net->B * 2 <= nb && nb > kn.lat_fuse_nb && kn.latency) fuse = false;
-            }
-            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
-            const UmmaEntry *e = find_umma(key);
-            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out) {
-                UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
-                key_so.stage_out = true;
-                const UmmaEntry *e_so = find_umma(key_so);
-                if (e_so) e = e_so;
-            }
-            int mt = 1;
-            if (e && !kn.no_mt2) {
-                // 256-row CTA tiles (two M tiles share each weight tile) when there is enough work for
-                // at least two waves of them; DNNB_MT2_MASK (bit i = block i) overrides per block
-                const long m_rows = fuse ? (long)((net->B + nb - 1) / nb) * nb * b.ih * b.iw : (long)net->B * b.ih * b.iw;
-                const long tiles2 = (m_rows + 255) / 256 * (ocp / bn);
-                // measured on B200 (TF32, batch 512): it pays when both accumulator stages survive
-                // (BN <= 128: block 3, 0.43 -> 0.28 ms) or when K is long enough to hide the serialised
-                // epilogue (block 7, K = 9216: 2.09 -> 1.98 ms; block 6, K = 4608, together with the tail
-                // launch below: 1.03 -> 1.00 ms and +1.4 % on the whole power-capped step, because a third
-                // less L2->SMEM traffic is also less energy); a loss for blocks 4-5
-                const long k_total = (long)b.kh * b.kw * b.ic;
-                bool want = tiles2 >= 2L * net->num_sms && (2 * bn <= 256 || k_total >= 4096);
-                if (kn.mt2_mask >= 0) want = (kn.mt2_mask >> i) & 1;
-                UmmaKey key2 = key;
-                key2.mt = 2;
-                const UmmaEntry *e2 = want ? find_umma(key2) : nullptr;
-                if (e2) { e = e2; mt = 2; }
-            }
-            if (e) {
-                b.umma = e;
-                b.family = fuse ? DNNB_KERNEL_UMMA_TILED : DNNB_KERNEL_UMMA_IM2COL;
-                b.pool_fused = fuse;
-                b.bn = bn;
-                b.swz = swz;
-                umma_conv::Params &p = b.up;
-                p = umma_conv::Params{};
-                p.H = b.ih; p.W = b.iw; p.B = net->B; p.OC = b.oc;
-                p.KH = b.kh; p.KW = b.kw; p.PT = b.pt; p.PL = b.pl;
-                p.c_chunks = c_chunks;
-                p.num_n_tiles = ocp / bn;
-                if (fuse) {
-                    p.tw = tw; p.th = th; p.nb = nb; p.log2_tw = ilog2(tw); p.log2_th = ilog2(th);
-                    p.tiles_w = b.iw / tw; p.tiles_h = b.ih / th;
-                    p.num_m_tiles = p.tiles_w * p.tiles_h * ((net->B + nb * mt - 1) / (nb * mt));
-                    p.OH = b.ih / 2; p.OW = b.iw / 2;
-                } else {
-                    p.tw = p.th = p.nb = 1;
-                    p.M_total = net->B * b.ih * b.iw;
-                    p.num_m_tiles = (p.M_total + umma_conv::kBM * mt - 1) / (umma_conv::kBM * mt);
-                    p.OH = b.ih; p.OW = b.iw;
-                }
-                p.leaky = b.leaky;
-                p.round_tf32 = b.round_tf32;
-                // split-K when the output tiles alone cannot occupy the SMs (small batches)
-                const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
-                const int kstages = total_kb / kbs;
-                p.splits = 1;
-                // Splitting costs ~7 us (partials through L2, sibling wait, reduction) and a CTA streams one ring
-                // of smem stages per ~2 us round trip, so a K loop of up to three ring passes stays whole
-                // (measured, batch 1: block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
-                const bool long_k = kstages > 3 * e->stages || kn.split_min_stages > 0;
-                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && long_k && kn.latency) {
-                    int sp = net->num_sms / tiles_mn;
-                    const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
-                    if (sp > kstages / min_stages) sp = kstages / min_stages;
-                    if (sp >= 2) p.splits = sp;
-                }
-                const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
-                b.grid = tiles < net->num_sms ? tiles : net->num_sms;
-                // CTA pairs (conv_pair.cuh, tcgen05.mma.cta_group::2) for the big im2col blocks: a third to a
-                // quarter less L2->SMEM traffic per flop.  The main launch covers whole waves of pair tiles;
-                // the remaining rows go to a tail launch of the single-CTA kernel in 128 x 128 tiles.
-                b.pair = nullptr;
-                b.umma_tail = nullptr;
-                const int sms = net->num_sms;
-                if (!fuse && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
-                    sms % 2 == 0 && !kn.no_pair) {
-                    // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
-                    // MT = 2 everywhere 82.8 k, no pairs 82.5 k -- two accumulator stages and six smem stages are
-                    // worth more than the last quarter of traffic
-                    const int pmt = kn.pair_mt;
-                    const PairEntry *pe = find_pair(in_bf16, b.out_bf16, pmt);
-                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
-                    const UmmaEntry *et = find_umma(kt);
-                    const int pairs = sms / 2;
-                    const int rows_per = 2 * pmt * umma_conv::kBM;
-                    const int m_all = p.M_total / rows_per;                 // whole pair tiles
-                    const int tiles_p = m_all * p.num_n_tiles;
-                    const int min_tiles = kn.pair_min_tiles >= 0 ? kn.pair_min_tiles : 2 * pairs;
-                    if (pe && et && tiles_p >= min_tiles && tiles_p > 0) {
-                        // stop at the last full wave when the partial one would be less than half full
-                        int main_m = m_all;
-                        if (tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs && !kn.pair_no_tail) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
-                        b.pair = pe;
-                        pairconv::Params &q = b.pp;
-                        q = pairconv::Params{};
-                        q.H = b.ih; q.W = b.iw; q.B = net->B; q.OC = b.oc;
-                        q.KH = b.kh; q.KW = b.kw; q.PT = b.pt; q.PL = b.pl;
-                        q.c_chunks = c_chunks;
-                        q.num_m_tiles = main_m; q.num_n_tiles = p.num_n_tiles;
-                        q.M_total = p.M_total; q.m_base = 0;
-                        q.leaky = b.leaky; q.round_tf32 = b.round_tf32;
-                        const int t = main_m * p.num_n_tiles;
-                        b.grid = 2 * (t < pairs ? t : pairs);
-                        int rows_done = main_m * rows_per;
-                        // whole pair tiles past the full waves: pairs again, in 256 x 128 tiles so that they
-                        // spread over twice as many pairs (block 7: 20 tiles -> 40 of the 74 pairs, 100 -> 50 us)
-                        b.pair_tail = nullptr;
-                        const PairEntry *pt = pmt == 1 ? find_pair(in_bf16, b.out_bf16, 1, 128) : nullptr;
-                        const int m_pt = (p.M_total - rows_done) / (2 * umma_conv::kBM);
-                        if (pt && m_pt > 0 && !kn.no_pair_tail) {
-                            b.pair_tail = pt;
-                            b.pp_tail = q;
-                            b.pp_tail.m_base = rows_done;
-                            b.pp_tail.num_m_tiles = m_pt;
-                            b.pp_tail.num_n_tiles = ocp / 128;
-                            const int tt = m_pt * (ocp / 128);
-                            b.grid_pair_tail = 2 * (tt < pairs ? tt : pairs);
-                            rows_done += m_pt * 2 * umma_conv::kBM;
-                        }
-                        const int rows_left = p.M_total - rows_done;
-                        if (rows_left > 0) {
-                            const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
-                            b.umma_tail = et;
-                            b.up_tail = p;
-                            b.up_tail.m_base = rows_done;
-                            b.up_tail.num_m_tiles = m_left;
-                            b.up_tail.num_n_tiles = ocp / 128;
-                            const int tt = m_left * (ocp / 128);
-                            b.grid_tail = tt < sms ? tt : sms;
-                        }
-                    }
-                }
-                // Without pairs: wave quantisation.  1352 tiles on 148 SMs are 9.14 waves and cost 10.  Cut the
-                // block into a main launch of whole waves and a tail launch over the remaining rows with tiles
-                // small enough to occupy every SM once.  Every output element still sums its K blocks in the same
-                // order, so results do not change (tests: batch invariance, 2 GPUs == 1 GPU).
-                // Measured: worth it for the 256 x 256 tiles (block 7: 1.98 -> 1.89 ms); 128 x 256 tiles cut any
-                // finer become L2-bandwidth bound and the tail costs as much as the wave it replaces.
-                if (!b.pair && !fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
-                    !kn.no_tail) {
-                    const int main_m = (tiles / sms) * sms / p.num_n_tiles;           // whole m-tiles in the full waves
-                    const int rows_left = p.M_total - main_m * mt * umma_conv::kBM;
-                    const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
-                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
-                    const UmmaEntry *et = find_umma(kt);
-                    const int t_tiles = m_left * (ocp / 128);
-                    if (et && 128 < bn * mt && ocp % 128 == 0 && t_tiles <= sms) {
-                        b.umma_tail = et;
-                        b.up_tail = p;
-                        b.up_tail.m_base = main_m * mt * umma_conv::kBM;
-                        b.up_tail.num_m_tiles = m_left;
-                        b.up_tail.num_n_tiles = ocp / 128;
-                        b.grid_tail = t_tiles;
-                        p.num_m_tiles = main_m;
-                    }
-                }
-            }
-        }
-    }
-    if (b.family == DNNB_KERNEL_SIMT)
-        b.pool_fused = b.pool_k == 2 && b.pool_s == 2 && b.ch % 2 == 0 && b.cw % 2 == 0;
-    b.pool_separate = b.pool_k > 0 && !b.pool_fused;
-}
 
 template <bool BF16, bool OUT_BF16, bool IN_U8 = false>
 cudaError_t launch_conv0_t(const conv0::Params &p, int grid, cudaStream_t st) {
