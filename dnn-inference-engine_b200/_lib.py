@@ -262,12 +262,12 @@ class Net:
         check(lib.dnnb_net_sync(self._h))
 
     def block_info(self, i):
-        info = (c_int * 12)()
+        info = (c_int * 13)()
         check(lib.dnnb_net_block_info(self._h, i, info))
         v = list(info)
         return {"kernel": KERNEL_NAMES[v[0]], "out_shape": (self.in_shape[0], v[1], v[2], v[3]),
                 "pool_fused": bool(v[4]), "bn_tile": v[5], "swizzle": v[6], "stages": v[7], "grid": v[8],
-                "pool_separate": bool(v[9]), "act_bytes": v[10], "launches": v[11]}
+                "pool_separate": bool(v[9]), "act_bytes": v[10], "launches": v[11], "tiles": v[12]}
 
     def block_output(self, i):
         shape = self.block_info(i)["out_shape"]

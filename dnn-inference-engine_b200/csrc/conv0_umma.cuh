@@ -81,8 +81,14 @@ struct Params {
     const float *scale;  // [16]
     const float *shift;  // [16]
     int B, H, W;         // H % 8 == 0, W % 4 == 0
-    int col_tiles;       // ceil(W / 128)
-    int num_tiles;       // B * (H/8) * col_tiles
+    int col_tiles;       // column tiles per row tile: ceil(W / 128), or W / 128 when the narrow remainder is packed
+    int num_tiles;       // B * tiles_per_image
+    // Packed narrow tiles (pack >= 2): W = 128 col_tiles + narrow.  Instead of a column tile that carries only
+    // `narrow` valid pixels through 128 MMA rows, the narrow right-hand parts of `pack` consecutive row tiles
+    // share one tile: segment s = MMA rows [seg_pitch s, seg_pitch s + narrow), seg_pitch = narrow + 2 (each
+    // segment has its own one-pixel halo in the patch).  An image is then (H/8) col_tiles ordinary tiles
+    // followed by ceil((H/8) / pack) packed ones.  416 columns: 174 tiles per image instead of 208.
+    int pack, seg_pitch, narrow, tiles_per_image;
     int leaky, round_tf32;
     int pool_first;      // every scale[c] > 0: scale/shift, LeakyReLU and rounding are then monotone, so the
                          // epilogue pools the raw accumulators and activates one value instead of four
@@ -139,22 +145,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_begin = (int)blockIdx.x * per_cta;
     const int my_tiles = max(0, min(p.num_tiles, tile_begin + per_cta) - tile_begin);
-    // tile -> (column tile ct, row tile jt, image n), advanced incrementally
+    // tile -> (column tile ct, row tile jt, image n), advanced incrementally.  With packing, ct == col_tiles
+    // marks a packed tile whose first row tile is jt.
     struct Coord { int ct, jt, n; };
     auto decode = [&](int tile) {
         Coord c;
-        c.ct = tile % p.col_tiles;
-        c.jt = (tile / p.col_tiles) % row_tiles;
-        c.n = tile / (p.col_tiles * row_tiles);
+        c.n = tile / p.tiles_per_image;
+        const int t = tile - c.n * p.tiles_per_image;
+        if (t < row_tiles * p.col_tiles) {
+            c.ct = t % p.col_tiles;
+            c.jt = t / p.col_tiles;
+        } else {
+            c.ct = p.col_tiles;
+            c.jt = (t - row_tiles * p.col_tiles) * p.pack;
+        }
         return c;
     };
     auto advance = [&](Coord &c, int steps) {
-        c.ct += steps;
-        while (c.ct >= p.col_tiles) {
-            c.ct -= p.col_tiles;
-            if (++c.jt == row_tiles) { c.jt = 0; ++c.n; }
+        for (int i = 0; i < steps; ++i) {
+            if (c.ct < p.col_tiles) {
+                if (++c.ct == p.col_tiles) {
+                    c.ct = 0;
+                    if (++c.jt == row_tiles) {
+                        c.jt = 0;
+                        if (p.pack) c.ct = p.col_tiles;       // the image's packed tiles follow
+                        else ++c.n;
+                    }
+                }
+            } else {
+                c.jt += p.pack;
+                if (c.jt >= row_tiles) { c.ct = 0; c.jt = 0; ++c.n; }
+            }
         }
     };
+    const int w0_packed = p.col_tiles * 128;
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ patch producers
@@ -183,21 +207,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             ptx::mbar_wait(bar_empty + 8 * stage, ((t / kStages) & 1) ^ 1);    // patch slot is free
             uint4 *patch = reinterpret_cast<uint4 *>(s_patch + stage * kPatchBytes);
             const uint8_t *raw = s_raw + slot * kRawBytes;
+            const bool packed = tc.ct == p.col_tiles;
 #pragma unroll
             for (int it = 0; it < kPxRounds; ++it) {
                 if (px_row[it] < kPatchRows) {
-                    const bool ok = (unsigned)(row0 + px_row[it]) < (unsigned)p.H && (unsigned)(w0 + px_col[it]) < (unsigned)p.W;
+                    bool ok;
+                    int src_off;
+                    if (!packed) {
+                        ok = (unsigned)(row0 + px_row[it]) < (unsigned)p.H && (unsigned)(w0 + px_col[it]) < (unsigned)p.W;
+                        src_off = px_src[it];
+                    } else {
+                        // patch pixel x = px_col + 4 belongs to segment (x - 3) / seg_pitch, its column cx there is
+                        // image column w0 - 1 + cx of row tile jt + segment; raw rows are stored [segment][row]
+                        constexpr int lead = IN_U8 ? kRawLeadU8 : 4, px_bytes = IN_U8 ? 3 : 12;
+                        const int xs = px_col[it] + 1;
+                        const int sg = xs >= 0 ? xs / p.seg_pitch : p.pack;
+                        const int cx = xs - sg * p.seg_pitch;
+                        const int irow = kTileRows * (tc.jt + sg) - 1 + px_row[it];
+                        ok = sg < p.pack && tc.jt + sg < row_tiles && (unsigned)irow < (unsigned)p.H &&
+                             (unsigned)(w0_packed - 1 + cx) < (unsigned)p.W;
+                        src_off = ((sg * kPatchRows + px_row[it]) * (p.narrow + 2 * lead) + cx - 1 + lead) * px_bytes;
+                    }
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);                        // outside the image: zeros (SAME padding)
                     if (ok) {
                         if constexpr (IN_U8) {
                             // the table holds the finished operand bits of float32(v / 255.)
-                            const uint8_t *src = raw + px_src[it];
+                            const uint8_t *src = raw + src_off;
                             const uint32_t v0 = s_lut[src[0]], v1 = s_lut[src[1]], v2 = s_lut[src[2]];
                             const uint32_t c0 = p.swap_rb ? v2 : v0, c2 = p.swap_rb ? v0 : v2;
                             if constexpr (BF16) { o.x = c0 | (v1 << 16); o.y = c2; }
                             else { o.x = c0; o.y = v1; o.z = c2; }
                         } else {
-                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + px_src[it]);
+                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + src_off);
                             const uint32_t f0 = src[0], f1 = src[1], f2 = src[2];
                             if constexpr (BF16) {
                                 __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f0), __uint_as_float(f1));
@@ -228,9 +269,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
                 const int slot = t % kRawDepth;
                 ptx::mbar_wait(bar_rempty + 8 * slot, ((t / kRawDepth) & 1) ^ 1);
-                const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
                 constexpr int lead = IN_U8 ? kRawLeadU8 : 4, span = IN_U8 ? kRawPxU8 : kPatchPx;
                 constexpr int px_bytes = IN_U8 ? 3 : 12, row_bytes = IN_U8 ? kRawRowBytesU8 : kRawRowBytes;
+                if (tc.ct == p.col_tiles) {
+                    // packed tile: per segment (row tile jt + sg) the rows of columns [w0 - lead, W), stored [segment][row]
+                    const int nseg = min(p.pack, row_tiles - tc.jt);
+                    const uint32_t bytes = (uint32_t)(p.W - (w0_packed - lead)) * px_bytes;     // a multiple of 16
+                    const int seg_row_bytes = (p.narrow + 2 * lead) * px_bytes;
+                    uint32_t rows = 0;
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        const int row0 = kTileRows * (tc.jt + sg) - 1;
+                        rows += (uint32_t)((row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0) - (row0 < 0 ? -row0 : 0));
+                    }
+                    ptx::mbar_expect_tx(bar_rfull + 8 * slot, bytes * rows);
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        const int row0 = kTileRows * (tc.jt + sg) - 1;
+                        const int r_lo = row0 < 0 ? -row0 : 0;
+                        const int r_hi = row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0;
+                        const uint8_t *src = static_cast<const uint8_t *>(p.in) +
+                                             (((size_t)tc.n * p.H + (row0 + r_lo)) * p.W + (w0_packed - lead)) * px_bytes;
+                        uint32_t dst = raw_base + slot * kRawBytes + (sg * kPatchRows + r_lo) * seg_row_bytes;
+                        for (int r = r_lo; r < r_hi; ++r, src += (size_t)p.W * px_bytes, dst += seg_row_bytes)
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_rfull + 8 * slot) : "memory");
+                    }
+                    continue;
+                }
+                const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
                 const int px_lo = w0 - lead > 0 ? w0 - lead : 0;
                 const int px_hi = w0 + span - lead < p.W ? w0 + span - lead : p.W;
                 const int r_lo = row0 < 0 ? -row0 : 0;
@@ -297,12 +362,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         for (int c = 0; c < 8; ++c) { sc8[c] = s_scale[(odd ? 8 : 0) + c]; sh8[c] = s_shift[(odd ? 8 : 0) + c]; }
         Coord tc = decode(tile_begin + group);
         for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
-            const int ct = tc.ct, jt = tc.jt, n = tc.n;
-            const int w = ct * 128 + m;
+            const int ct = tc.ct, n = tc.n;
+            int jt = tc.jt, w = ct * 128 + m;
+            bool valid = w < p.W;
+            const bool packed = ct == p.col_tiles;
+            if (packed) {                              // lane m = segment m / seg_pitch, column m % seg_pitch of row tile jt + segment
+                const int sg = m / p.seg_pitch, cx = m - sg * p.seg_pitch;
+                jt += sg;
+                w = w0_packed + cx;
+                valid = sg < p.pack && cx < p.narrow && jt < row_tiles;
+            }
             const int acc = t % kAccStages;
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / kAccStages) & 1);
             ptx::tc_fence_after();
-            if (ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
+            if (packed || ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
 #pragma unroll 1
                 for (int rp = 0; rp < kTileRows / 2; ++rp) {      // pooling row pairs of the tile
                     uint32_t raw[32];                             // [0,16): output row 2rp, [16,32): row 2rp+1
@@ -316,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                             if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
                             if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
                             else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
-                            if (w < p.W) {
+                            if (valid) {
                                 p.prepool[(((size_t)n * p.H + orow) * p.W + w) * 16 + c] = a;
                                 p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * 16 + c] = b;
                             }
@@ -358,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                             r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));   // horizontal max: columns w, w^1
                         }
                     }
-                    if (w < p.W) {
+                    if (valid) {
                         const size_t pix = ((size_t)n * OH + (orow >> 1)) * OW + (w >> 1);
                         if constexpr (OUT_BF16) {
                             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + pix * 16 + (odd ? 8 : 0);

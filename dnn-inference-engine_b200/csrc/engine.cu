@@ -974,6 +974,10 @@ int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
     info[9] = b.pool_separate ? 1 : 0;
     info[10] = b.out_bf16 ? 2 : 4;
     info[11] = 1 + (b.pool_separate ? 1 : 0) + (b.umma_tail ? 1 : 0) + (b.pair_tail ? 1 : 0);
+    info[12] = b.family == DNNB_KERNEL_UMMA_CONV0 ? b.c0.num_tiles
+               : b.family == DNNB_KERNEL_UMMA_ROWPAIR ? b.rp.num_tiles
+               : b.pair ? b.pp.num_m_tiles * b.pp.num_n_tiles
+               : b.umma ? b.up.num_m_tiles * b.up.num_n_tiles * b.up.splits : 0;
     return 0;
 }
 

@@ -145,9 +145,9 @@ int dnnb_net_block_output(dnnb_net *net, int block, float *host_out);
  * output is rewritten with identical values. */
 int dnnb_net_debug_prepool(dnnb_net *net, int block, float *host_out);
 
-/* info[0..11] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
+/* info[0..12] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
  * epilogue), BN tile, swizzle bytes, stages, grid, separate-pool-kernel(0/1), elem bytes of the
- * stored activation, launches per forward} */
+ * stored activation, launches per forward, work items (tiles) of the main launch} */
 int dnnb_net_block_info(dnnb_net *net, int block, int *info);
 
 /* Times each block's kernels with CUDA events on the network's stream: `iters` timed
