@@ -394,7 +394,7 @@ def test_latency_mode_split_k_stays_within_reordering_noise(oracle_libs, monkeyp
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 def test_latency_mode_graph_replay_equals_direct_launches(monkeypatch, precision):
     """DNNB_LATENCY_MODE=1 also chains the kernels by programmatic dependent launch and replays the
-    device-resident forward (dnnb_net_forward_device) from a CUDA graph from the third call on the same
+    device-resident forward (dnnb_net_forward_device) from a CUDA graph from the second call on the same
     pointers.  Every replay must reproduce the directly launched result bit for bit -- the split-K
     counters reset themselves on the device -- also after the input buffer's contents change, and the
     graph-free, PDL-free launch sequence (DNNB_NO_GRAPH, DNNB_NO_PDL) must give the same bits."""
@@ -419,7 +419,7 @@ def test_latency_mode_graph_replay_equals_direct_launches(monkeypatch, precision
         eng.close()
         return outs
 
-    outs = run_all(12)                          # calls 0-1 direct, call 1 captured, 2.. replayed
+    outs = run_all(12)                          # call 0 direct; call 1 (the buffer pair again) is captured and replayed, as are 2..
     monkeypatch.setenv("DNNB_NO_GRAPH", "1")
     monkeypatch.setenv("DNNB_NO_PDL", "1")
     plain = run_all(2)
