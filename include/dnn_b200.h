@@ -94,7 +94,8 @@ int dnnb_net_add_block(dnnb_net *net, const float *kernel, int kh, int kw, int i
  * Environment, read here: DNNB_LATENCY_MODE=1 plans for small-batch latency -- split-K over co-resident
  * CTAs (deterministic, but a different fp32 summation order than the default plan), kernels chained by
  * programmatic dependent launch, and dnnb_net_forward_device replayed from a CUDA graph per
- * (dev_in, dev_out) pair from the second call on (the first one launches directly and sets function attributes and tensor maps) (DNNB_NO_PDL / DNNB_NO_GRAPH switch the last two off). */
+ * (dev_in, dev_out) pair from the second call on (the first call launches directly and sets function
+ * attributes and tensor maps).  DNNB_NO_PDL / DNNB_NO_GRAPH switch the last two off. */
 int dnnb_net_finalize(dnnb_net *net);
 
 int dnnb_net_num_blocks(dnnb_net *net, int *n);
