@@ -160,11 +160,7 @@ def batch1_latency(_lib, spec, precision, device, forwards=100, warmup=10):
     (DNNB_LATENCY_MODE=1: split-K over co-resident CTAs, kernels chained by programmatic dependent launch,
     the launch sequence replayed from a CUDA graph).  Each forward is timed on its own with CUDA events."""
     import torch
-    os.environ["DNNB_LATENCY_MODE"] = "1"
-    try:
-        net = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device)
-    finally:
-        os.environ.pop("DNNB_LATENCY_MODE", None)
+    net = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device, latency=True)
     dev = torch.device("cuda", device)
     stream = torch.cuda.current_stream(dev)
     x = torch.rand((1, 416, 416, 3), device=dev)

@@ -143,11 +143,15 @@ class Net:
     """Resident fused network (dnnb_net_*).  blocks: list of dicts with keys kernel, padding,
     biases, mean, variance, gamma, epsilon, leaky, pool (None or (k, s, padding))."""
 
-    def __init__(self, in_shape, blocks, precision="tf32", device=0):
+    def __init__(self, in_shape, blocks, precision="tf32", device=0, latency=None):
+        """latency: True / False selects the small-batch latency plan for this network (split-K, PDL chain,
+        CUDA-graph replay; include/dnn_b200.h, dnnb_net_finalize) regardless of DNNB_LATENCY_MODE; None leaves
+        the choice to the environment."""
         b, h, w, c = (int(v) for v in in_shape)
         self.in_shape = (b, h, w, c)
         self.precision = precision
         self.device = device
+        self.latency = latency
         self._h = c_void_p()
         check(lib.dnnb_net_create(device, PRECISIONS[precision], b, h, w, c, ctypes.byref(self._h)))
         try:
@@ -162,7 +166,17 @@ class Net:
                 check(lib.dnnb_net_add_block(self._h, fptr(k), kh, kw, ic, oc, 1 if blk.get("padding", 'SAME') == 'SAME' else 0,
                                              p(bias), p(mean), p(var), p(gamma), float(blk.get("epsilon", 0.0)),
                                              1 if blk.get("leaky") else 0, pk, ps, pp))
-            check(lib.dnnb_net_finalize(self._h))
+            saved = os.environ.get("DNNB_LATENCY_MODE")
+            if latency is not None:                  # the library reads the switch when it plans the network
+                os.environ["DNNB_LATENCY_MODE"] = "1" if latency else "0"
+            try:
+                check(lib.dnnb_net_finalize(self._h))
+            finally:
+                if latency is not None:
+                    if saved is None:
+                        os.environ.pop("DNNB_LATENCY_MODE", None)
+                    else:
+                        os.environ["DNNB_LATENCY_MODE"] = saved
             o = [c_int(0) for _ in range(4)]
             check(lib.dnnb_net_out_shape(self._h, *[ctypes.byref(v) for v in o]))
             self.out_shape = tuple(v.value for v in o)

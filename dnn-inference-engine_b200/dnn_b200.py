@@ -34,11 +34,12 @@ F32_MIN = np.finfo(np.float32).min
 
 
 class DnnInferenceEngine(object):
-    def __init__(self, graph, debug=False, precision="tf32", device=0):
+    def __init__(self, graph, debug=False, precision="tf32", device=0, latency=None):
         self.g = graph
         self.debug = debug
         self.precision = precision
         self.device = device
+        self.latency = latency       # True: plan for single-image latency (see _lib.Net); None: DNNB_LATENCY_MODE decides
         self.save_dir = os.path.join(os.getcwd(), "intermediate")
         self._net = None
         self._net_key = None
@@ -102,7 +103,7 @@ class DnnInferenceEngine(object):
                 "leaky": "leaky" in blk,
                 "pool": None if pool is None else (pool.ksize[1], pool.strides[1], pool.padding),
             })
-        return _lib.Net(self.g.in_node.in_shape, spec, precision=self.precision, device=self.device)
+        return _lib.Net(self.g.in_node.in_shape, spec, precision=self.precision, device=self.device, latency=self.latency)
 
     def run(self, tin):
         self.g.in_node.set_input(tin)

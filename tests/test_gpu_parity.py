@@ -430,6 +430,34 @@ def test_latency_mode_graph_replay_equals_direct_launches(monkeypatch, precision
     assert normalised_error(outs[0], gold) < TOL[precision]
 
 
+def test_latency_keyword_equals_the_environment_switch(monkeypatch):
+    """DnnInferenceEngine(..., latency=True) plans like DNNB_LATENCY_MODE=1 without touching the caller's
+    environment; latency=False overrides the variable the other way."""
+    x = make_images(1, seed=100)
+
+    def run(**kw):
+        g = dnn_b200.DnnGraphBuilder()
+        build_yolov2tiny(g, [1, 416, 416, 3], make_weights(0))
+        eng = dnn_b200.DnnInferenceEngine(g, False, precision="tf32", **kw)
+        out = eng.run(x).copy()
+        tiles = [p["tiles"] for p in eng.kernel_plan()]
+        eng.close()
+        return out, tiles
+
+    monkeypatch.delenv("DNNB_LATENCY_MODE", raising=False)
+    out_default, tiles_default = run()
+    out_kw, tiles_kw = run(latency=True)
+    assert "DNNB_LATENCY_MODE" not in os.environ
+    monkeypatch.setenv("DNNB_LATENCY_MODE", "1")
+    out_env, tiles_env = run()
+    out_off, tiles_off = run(latency=False)
+    assert os.environ["DNNB_LATENCY_MODE"] == "1"
+    assert tiles_kw == tiles_env and tiles_kw != tiles_default and tiles_off == tiles_default
+    assert tiles_kw[7] > 100 > tiles_default[7]          # block 7 is split over (nearly) all SMs
+    np.testing.assert_array_equal(out_kw, out_env)
+    np.testing.assert_array_equal(out_off, out_default)
+
+
 def test_uint8_frames_match_numpy_preprocessing():
     """proj3/__init__.py:8-12 minus the resize.  The device-side /255 + BGR->RGB must be
     bit-identical to numpy's, so the network output equals the float32 path's exactly."""
