@@ -46,6 +46,8 @@ _sig("dnnb_net_create", c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER
 _sig("dnnb_net_add_block", c_void_p, FP, c_int, c_int, c_int, c_int, c_int, FP, FP, FP, FP, c_float,
      c_int, c_int, c_int, c_int)
 _sig("dnnb_net_finalize", c_void_p)
+_sig("dnnb_net_set_latency", c_void_p, c_int)
+_sig("dnnb_net_knobs", c_void_p, ctypes.c_char_p, c_int)
 _sig("dnnb_net_num_blocks", c_void_p, IP)
 _sig("dnnb_net_out_shape", c_void_p, IP, IP, IP, IP)
 _sig("dnnb_net_forward", c_void_p, c_void_p, c_void_p)
@@ -54,6 +56,8 @@ _sig("dnnb_net_forward_device", c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("dnnb_net_forward_u8_async", c_void_p, c_void_p, c_int, c_void_p)
 _sig("dnnb_net_forward_u8_device", c_void_p, c_void_p, c_int, c_void_p, c_void_p)
 _sig("dnnb_net_sync", c_void_p)
+_sig("dnnb_net_next_slot", c_void_p, IP)
+_sig("dnnb_net_wait_slot", c_void_p, c_int)
 _sig("dnnb_net_block_output", c_void_p, c_int, FP)
 _sig("dnnb_net_block_info", c_void_p, c_int, IP)
 _sig("dnnb_net_debug_prepool", c_void_p, c_int, FP)
@@ -80,8 +84,10 @@ _sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 
 EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
+           "dnnb_net_set_latency", "dnnb_net_knobs",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
-           "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
+           "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync",
+           "dnnb_net_next_slot", "dnnb_net_wait_slot", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
            "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit",
            "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
@@ -107,6 +113,20 @@ def fptr(a):
 def f32c(a):
     """float32, C-contiguous view/copy (the reference hands numpy buffers to C as float*)."""
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def require_buffer(a, dtype, shape, what):
+    """The async entry points hand raw pointers to cudaMemcpyAsync: anything but a C-contiguous array of exactly
+    the expected dtype and shape would be read or written out of bounds, so it is rejected here."""
+    if not isinstance(a, np.ndarray):
+        raise TypeError("%s must be a numpy array, got %s" % (what, type(a).__name__))
+    if a.dtype != np.dtype(dtype):
+        raise TypeError("%s must be %s, got %s" % (what, np.dtype(dtype), a.dtype))
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(a.shape)))
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("%s must be C-contiguous" % what)
+    return a
 
 
 def device_count():
@@ -166,17 +186,9 @@ class Net:
                 check(lib.dnnb_net_add_block(self._h, fptr(k), kh, kw, ic, oc, 1 if blk.get("padding", 'SAME') == 'SAME' else 0,
                                              p(bias), p(mean), p(var), p(gamma), float(blk.get("epsilon", 0.0)),
                                              1 if blk.get("leaky") else 0, pk, ps, pp))
-            saved = os.environ.get("DNNB_LATENCY_MODE")
-            if latency is not None:                  # the library reads the switch when it plans the network
-                os.environ["DNNB_LATENCY_MODE"] = "1" if latency else "0"
-            try:
-                check(lib.dnnb_net_finalize(self._h))
-            finally:
-                if latency is not None:
-                    if saved is None:
-                        os.environ.pop("DNNB_LATENCY_MODE", None)
-                    else:
-                        os.environ["DNNB_LATENCY_MODE"] = saved
+            if latency is not None:
+                check(lib.dnnb_net_set_latency(self._h, 1 if latency else 0))
+            check(lib.dnnb_net_finalize(self._h))
             o = [c_int(0) for _ in range(4)]
             check(lib.dnnb_net_out_shape(self._h, *[ctypes.byref(v) for v in o]))
             self.out_shape = tuple(v.value for v in o)
@@ -203,11 +215,14 @@ class Net:
         assert tuple(x.shape) == self.in_shape, (x.shape, self.in_shape)
         if out is None:
             out = np.empty(self.out_shape, dtype=np.float32)
+        require_buffer(out, np.float32, self.out_shape, "out")
         check(lib.dnnb_net_forward(self._h, x.ctypes.data, out.ctypes.data))
         return out
 
     def forward_async(self, x, out):
         """x, out: C-contiguous float32 arrays (ideally PinnedArray.array) kept alive until sync()."""
+        require_buffer(x, np.float32, self.in_shape, "x")
+        require_buffer(out, np.float32, self.out_shape, "out")
         check(lib.dnnb_net_forward_async(self._h, x.ctypes.data, out.ctypes.data))
 
     def forward_u8(self, frames, bgr=True, out=None):
@@ -228,12 +243,15 @@ class Net:
         assert frames.ndim == 4 and frames.shape[0] == self.in_shape[0] and frames.shape[3] == 3, frames.shape
         if out is None:
             out = np.empty(self.out_shape, dtype=np.float32)
+        require_buffer(out, np.float32, self.out_shape, "out")
         check(lib.dnnb_net_forward_frames_async(self._h, frames.ctypes.data, frames.shape[1], frames.shape[2],
                                                 1 if bgr else 0, out.ctypes.data))
         self.sync()
         return out
 
     def forward_u8_async(self, frames, out, bgr=True):
+        require_buffer(frames, np.uint8, self.in_shape, "frames")
+        require_buffer(out, np.float32, self.out_shape, "out")
         check(lib.dnnb_net_forward_u8_async(self._h, frames.ctypes.data, 1 if bgr else 0, out.ctypes.data))
 
     def set_detect(self, score_threshold=0.3, iou_threshold=0.3, max_det=32):
@@ -243,13 +261,16 @@ class Net:
     def detect_async(self, x, dets, counts, bgr=True):
         """Forward + on-device box decoding.  x: float32 [B,H,W,C] or uint8 frames; dets: DET_DTYPE
         [B, max_det]; counts: int32 [B] (ideally PinnedArray.array), kept alive until sync()."""
-        assert dets.dtype == DET_DTYPE and dets.shape == (self.in_shape[0], getattr(self, "max_det", 32))
-        assert counts.dtype == np.int32 and counts.shape == (self.in_shape[0],)
-        if x.dtype == np.uint8:
+        require_buffer(dets, DET_DTYPE, (self.in_shape[0], getattr(self, "max_det", 32)), "dets")
+        require_buffer(counts, np.int32, (self.in_shape[0],), "counts")
+        if isinstance(x, np.ndarray) and x.dtype == np.uint8:
+            require_buffer(x, np.uint8, None, "frames")
+            if x.ndim != 4 or x.shape[0] != self.in_shape[0] or x.shape[3] != 3:
+                raise ValueError("frames must be [%d, h, w, 3], got %s" % (self.in_shape[0], tuple(x.shape)))
             check(lib.dnnb_net_detect_frames_async(self._h, x.ctypes.data, x.shape[1], x.shape[2], 1 if bgr else 0,
                                                    dets.ctypes.data, counts.ctypes.data))
         else:
-            assert x.dtype == np.float32
+            require_buffer(x, np.float32, self.in_shape, "x")
             check(lib.dnnb_net_detect_async(self._h, x.ctypes.data, dets.ctypes.data, counts.ctypes.data))
 
     def detect(self, x, bgr=True):
@@ -274,6 +295,16 @@ class Net:
 
     def sync(self):
         check(lib.dnnb_net_sync(self._h))
+
+    def next_slot(self):
+        """Pipeline slot (0 / 1) the next *_async call will use."""
+        n = c_int(0)
+        check(lib.dnnb_net_next_slot(self._h, ctypes.byref(n)))
+        return n.value
+
+    def wait_slot(self, slot):
+        """Blocks until the most recent job queued on `slot` has delivered its results to the host buffers."""
+        check(lib.dnnb_net_wait_slot(self._h, slot))
 
     def block_info(self, i):
         info = (c_int * 13)()
@@ -311,6 +342,14 @@ class Net:
 
     def debug_block_limit(self, blocks):
         check(lib.dnnb_net_debug_block_limit(self._h, blocks))
+
+    def knobs(self):
+        """The DNNB_* switches that were not at their default when this network was planned, as a dict
+        (empty for the default plan); an explicit latency= argument shows up as 'set_latency'."""
+        buf = ctypes.create_string_buffer(4096)
+        check(lib.dnnb_net_knobs(self._h, buf, len(buf)))
+        text = buf.value.decode()
+        return dict(item.split("=", 1) for item in text.split(",")) if text else {}
 
     def launches_per_forward(self):
         n = c_int(0)

@@ -224,6 +224,30 @@ int capture_forward(dnnb_net *net, const void *dev_in, void *dev_out, cudaStream
     return 0;
 }
 
+// The device-entry calls (dnnb_net_forward_device with dev_out == NULL, forward_u8_device, detect_device) use
+// slot 0 of the host pipeline's double buffers: d_in2[0] as fp32 staging and the last block's own buffer
+// (= d_outf[0]) as the result.  They order themselves after the H2D / D2H copies the *_async calls still have
+// in flight on those buffers, and publish their own completion to the pipeline the same way.
+bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return true; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+// (a caller capturing the call into its own graph orders it itself: events from outside a capture cannot be waited on)
+int slot0_acquire(dnnb_net *net, cudaStream_t st, bool uses_in, bool uses_out) {
+    if ((!uses_in && !uses_out) || stream_is_capturing(st)) return 0;
+    if (uses_in) CK(cudaStreamWaitEvent(st, net->in_free[0], 0));
+    if (uses_in) CK(cudaStreamWaitEvent(st, net->in_ready[0], 0));
+    if (uses_out) CK(cudaStreamWaitEvent(st, net->out_free[0], 0));
+    return 0;
+}
+int slot0_release(dnnb_net *net, cudaStream_t st, bool uses_in, bool uses_out) {
+    if ((!uses_in && !uses_out) || stream_is_capturing(st)) return 0;
+    if (uses_in) CK(cudaEventRecord(net->in_free[0], st));
+    if (uses_out) CK(cudaEventRecord(net->out_free[0], st));
+    return 0;
+}
+
 int check_net(dnnb_net *net, bool need_final) {
     if (!net) return fail("null network handle");
     if (need_final && !net->finalized) return fail("network not finalized");
@@ -414,7 +438,13 @@ int dnnb_net_finalize(dnnb_net *net) {
     int h = net->H, w = net->W;
     bool in_bf16 = false;
     net->launches = 0;
-    net->knobs = read_knobs();
+    {
+        std::string err;
+        if (read_knobs(net->knobs, net->knobs_active, err)) return fail("%s", err.c_str());
+        if (net->latency_override >= 0) {        // dnnb_net_set_latency wins over DNNB_LATENCY_MODE
+            net->knobs.latency = net->latency_override != 0;
+        }
+    }
     net->pdl = net->knobs.latency && !net->knobs.no_pdl;
     net->use_graph = net->knobs.latency && !net->knobs.no_graph;
     for (size_t i = 0; i < net->blocks.size(); ++i) {
@@ -581,16 +611,21 @@ int dnnb_net_out_shape(dnnb_net *net, int *b, int *h, int *w, int *c) {
 int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, void *stream) {
     if (check_net(net, true)) return 1;
     if (!dev_in) return fail("null device input");
+    // TMA tensor maps, bulk copies and the vector stores of the epilogues need 16-byte aligned tensors
+    if ((reinterpret_cast<uintptr_t>(dev_in) & 15) || (reinterpret_cast<uintptr_t>(dev_out) & 15))
+        return fail("dev_in and dev_out must be 16-byte aligned");
     DeviceGuard g(net->device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
     net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
     net->last_in = dev_in;
+    const bool own_out = dev_out == nullptr;
+    if (own_out && slot0_acquire(net, st, false, true)) return 1;
     if (net->use_graph && net->prof_block < 0) {
         for (dnnb_net::GraphSlot &g : net->graphs)
             if (g.in == dev_in && g.out == dev_out) {
                 g.used = ++net->graph_tick;
                 CK(cudaGraphLaunch(g.exec, st));
-                return 0;
+                return own_out ? slot0_release(net, st, false, true) : 0;
             }
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (net->warm_in == dev_in && net->warm_out == dev_out && cudaStreamIsCapturing(st, &cs) == cudaSuccess &&
@@ -608,14 +643,15 @@ int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, vo
                 g.in = dev_in; g.out = dev_out; g.exec = exec; g.used = ++net->graph_tick;
                 net->graphs.push_back(g);
                 CK(cudaGraphLaunch(exec, st));
-                return 0;
+                return own_out ? slot0_release(net, st, false, true) : 0;
             }
             net->use_graph = false;       // capture is not available here (legacy stream, driver): launch directly from now on
         }
         net->warm_in = dev_in;
         net->warm_out = dev_out;
     }
-    return forward_impl(net, dev_in, dev_out, st);
+    if (forward_impl(net, dev_in, dev_out, st)) return 1;
+    return own_out ? slot0_release(net, st, false, true) : 0;
 }
 
 namespace {
@@ -715,14 +751,18 @@ cudaError_t launch_preprocess(dnnb_net *net, const uint8_t *dev_u8, float *dev_f
 int dnnb_net_forward_u8_device(dnnb_net *net, const void *dev_u8, int bgr, void *dev_out, void *stream) {
     if (check_net(net, true)) return 1;
     if (!dev_u8) return fail("null device input");
+    if ((reinterpret_cast<uintptr_t>(dev_u8) & 15) || (reinterpret_cast<uintptr_t>(dev_out) & 15))
+        return fail("dev_u8 and dev_out must be 16-byte aligned");
     DeviceGuard g(net->device);
     if (ensure_u8(net)) return 1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
     const bool fused = u8_fused(net, 0, 0);
+    if (slot0_acquire(net, st, !fused, dev_out == nullptr)) return 1;
     if (!fused) CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_u8), net->d_in2[0], bgr ? 1 : 0, st));
     net->last_final = dev_out ? nullptr : static_cast<const float *>(net->blocks.back().d_out);
     net->last_in = fused ? nullptr : net->d_in2[0];
-    return fused ? forward_impl(net, dev_u8, dev_out, st, true, bgr ? 1 : 0) : forward_impl(net, net->d_in2[0], dev_out, st);
+    if (fused ? forward_impl(net, dev_u8, dev_out, st, true, bgr ? 1 : 0) : forward_impl(net, net->d_in2[0], dev_out, st)) return 1;
+    return slot0_release(net, st, !fused, dev_out == nullptr);
 }
 
 namespace {
@@ -889,6 +929,7 @@ int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr
                            void *stream) {
     if (check_net(net, true)) return 1;
     if (!dev_in || !dev_dets || !dev_counts) return fail("null device buffer");
+    if (reinterpret_cast<uintptr_t>(dev_in) & 15) return fail("dev_in must be 16-byte aligned");
     DeviceGuard g(net->device);
     if (ensure_detect(net)) return 1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : net->stream;
@@ -897,16 +938,18 @@ int dnnb_net_detect_device(dnnb_net *net, const void *dev_in, int is_u8, int bgr
     if (is_u8) {
         if (ensure_u8(net)) return 1;
         fused = u8_fused(net, 0, 0);
-        if (!fused) {
-            CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_in), net->d_in2[0], bgr ? 1 : 0, st));
-            in = net->d_in2[0];
-        }
+    }
+    const bool stage = is_u8 && !fused;
+    if (slot0_acquire(net, st, stage, true)) return 1;
+    if (stage) {
+        CK(launch_preprocess(net, static_cast<const uint8_t *>(dev_in), net->d_in2[0], bgr ? 1 : 0, st));
+        in = net->d_in2[0];
     }
     net->last_final = static_cast<const float *>(net->blocks.back().d_out);
     net->last_in = fused ? nullptr : in;
     if (forward_impl(net, in, nullptr, st, fused, bgr ? 1 : 0)) return 1;
     CK(launch_detect(net, net->last_final, dev_dets, dev_counts, st));
-    return 0;
+    return slot0_release(net, st, stage, true);
 }
 
 int dnnb_net_sync(dnnb_net *net) {
@@ -915,6 +958,20 @@ int dnnb_net_sync(dnnb_net *net) {
     CK(cudaStreamSynchronize(net->stream));
     if (net->copy_in) CK(cudaStreamSynchronize(net->copy_in));
     if (net->copy_out) CK(cudaStreamSynchronize(net->copy_out));
+    return 0;
+}
+
+int dnnb_net_next_slot(dnnb_net *net, int *slot) {
+    if (check_net(net, true) || !slot) return fail("bad argument");
+    *slot = net->flip;
+    return 0;
+}
+
+int dnnb_net_wait_slot(dnnb_net *net, int slot) {
+    if (check_net(net, true)) return 1;
+    if (slot < 0 || slot > 1) return fail("slot must be 0 or 1");
+    DeviceGuard g(net->device);
+    CK(cudaEventSynchronize(net->out_free[slot]));      // recorded after the slot's D2H copies
     return 0;
 }
 
@@ -1042,6 +1099,26 @@ int dnnb_net_profile_read(dnnb_net *net, float *total_ms, int *count) {
 int dnnb_net_launches_per_forward(dnnb_net *net, int *n) {
     if (check_net(net, true) || !n) return fail("bad argument");
     *n = net->launches;
+    return 0;
+}
+
+int dnnb_net_set_latency(dnnb_net *net, int mode) {
+    if (check_net(net, false)) return 1;
+    if (net->finalized) return fail("dnnb_net_set_latency must be called before dnnb_net_finalize");
+    if (mode < -1 || mode > 1) return fail("mode must be -1 (environment decides), 0 or 1");
+    net->latency_override = mode;
+    return 0;
+}
+
+int dnnb_net_knobs(dnnb_net *net, char *buf, int buf_len) {
+    if (check_net(net, true) || !buf || buf_len < 1) return fail("bad argument");
+    std::string text = net->knobs_active;
+    if (net->latency_override >= 0) {
+        if (!text.empty()) text += ",";
+        text += std::string("set_latency=") + (net->latency_override ? "1" : "0");
+    }
+    if ((int)text.size() + 1 > buf_len) return fail("buffer too small: %zu bytes needed", text.size() + 1);
+    memcpy(buf, text.c_str(), text.size() + 1);
     return 0;
 }
 

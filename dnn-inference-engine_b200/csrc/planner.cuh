@@ -3,11 +3,15 @@
 // activations and weights, and plan_block(), which decides for every conv block of
 // proj3/yolov2tiny.py:30-77 which kernel runs it, with which tiles, and how its tail rows are cut.
 #pragma once
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../include/dnn_b200.h"
 #include "conv0_umma.cuh"
 #include "launchers.cuh"
+
+extern "C" char **environ;
 
 namespace {
 
@@ -38,36 +42,102 @@ struct Knobs {
     int lat_fuse_nb = 0;             // DNNB_LAT_FUSE_NB      latency plan: keep fused spatial tiles up to this many images
     int split_min_stages = 0;        // DNNB_SPLIT_MIN_STAGES latency plan: K blocks per split (0: default 4, short loops whole)
     bool no_u8_fusion = false;       // DNNB_NO_U8_FUSION     uint8 frames through a separate preprocessing kernel
+    bool no_pool1_fusion = false;    // DNNB_NO_POOL1_FUSION  block 5: the stride-1 SAME pool as a separate kernel
+    bool no_cluster_splitk = false;  // DNNB_NO_CLUSTER_SPLITK latency plan: split-K through the global workspace, not cluster DSMEM
+    bool no_tma_store = false;       // DNNB_NO_TMA_STORE     epilogues store with per-thread st.global instead of bulk copies
+    bool no_l2_prefetch = false;     // DNNB_NO_L2_PREFETCH   latency plan: no L2 prefetch of the later blocks' weights
 };
 
-Knobs read_knobs() {
-    auto flag = [](const char *name) { return getenv(name) != nullptr; };
-    auto num = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
-    Knobs k;
-    const char *lat = getenv("DNNB_LATENCY_MODE");
-    k.latency = lat && lat[0] == '1';
-    k.no_pdl = flag("DNNB_NO_PDL");
-    k.no_graph = flag("DNNB_NO_GRAPH");
-    k.force_simt = flag("DNNB_FORCE_SIMT");
-    k.no_conv0 = flag("DNNB_NO_CONV0");
-    k.conv0_pack = num("DNNB_CONV0_PACK", 0) != 0;
-    k.no_rowpair = flag("DNNB_NO_ROWPAIR");
-    k.rowpair_linear = flag("DNNB_ROWPAIR_LINEAR") ? (num("DNNB_ROWPAIR_LINEAR", 0) != 0) : flag("DNNB_NO_ROWPAIR_LINEAR") ? 0 : -1;
-    k.rowpair_max_tr = num("DNNB_ROWPAIR_MAX_TR", 8);
-    k.no_pool_first = flag("DNNB_NO_POOL_FIRST");
-    k.no_stage_out = flag("DNNB_NO_STAGE_OUT");
-    k.no_mt2 = flag("DNNB_NO_MT2");
-    k.mt2_mask = num("DNNB_MT2_MASK", -1);
-    k.no_pair = flag("DNNB_NO_PAIR");
-    k.pair_mt = num("DNNB_PAIR_MT", 1) == 2 ? 2 : 1;
-    k.pair_min_tiles = num("DNNB_PAIR_MIN_TILES", -1);
-    k.pair_no_tail = flag("DNNB_PAIR_NO_TAIL");
-    k.no_pair_tail = flag("DNNB_NO_PAIR_TAIL");
-    k.no_tail = flag("DNNB_NO_TAIL");
-    k.lat_fuse_nb = num("DNNB_LAT_FUSE_NB", 0);
-    k.split_min_stages = num("DNNB_SPLIT_MIN_STAGES", 0);
-    k.no_u8_fusion = flag("DNNB_NO_U8_FUSION");
-    return k;
+// Every DNNB_* variable the library understands.  Anything else that starts with DNNB_ is a typo or a stale
+// switch from another build and makes dnnb_net_finalize fail (a stray variable must not silently change the
+// plan a benchmark measures).  Flags: present (empty or "1") = on, "0" = off.  Numbers: decimal, within [lo, hi].
+struct KnobDef {
+    const char *name;
+    bool is_flag;
+    int lo, hi;
+};
+const KnobDef g_knob_defs[] = {
+    {"DNNB_LATENCY_MODE", true, 0, 1},     {"DNNB_NO_PDL", true, 0, 1},          {"DNNB_NO_GRAPH", true, 0, 1},
+    {"DNNB_FORCE_SIMT", true, 0, 1},       {"DNNB_NO_CONV0", true, 0, 1},        {"DNNB_CONV0_PACK", true, 0, 1},
+    {"DNNB_NO_ROWPAIR", true, 0, 1},       {"DNNB_ROWPAIR_LINEAR", true, 0, 1},  {"DNNB_NO_ROWPAIR_LINEAR", true, 0, 1},
+    {"DNNB_ROWPAIR_MAX_TR", false, 2, 8},  {"DNNB_NO_POOL_FIRST", true, 0, 1},   {"DNNB_NO_STAGE_OUT", true, 0, 1},
+    {"DNNB_NO_MT2", true, 0, 1},           {"DNNB_MT2_MASK", false, 0, 1 << 20}, {"DNNB_NO_PAIR", true, 0, 1},
+    {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1},
+    {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
+    {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
+    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_NO_L2_PREFETCH", true, 0, 1},
+};
+
+// Reads the switches.  `active` receives "NAME=value" for every switch that is set to something other than
+// its default, comma separated (dnnb_net_knobs reports it; bench.py records it and refuses to publish a
+// headline number with any of them set).  Returns non-zero with `err` filled for an unknown DNNB_* name or
+// a value that does not parse.
+int read_knobs(Knobs &k, std::string &active, std::string &err) {
+    active.clear();
+    for (char **e = environ; e && *e; ++e) {
+        if (strncmp(*e, "DNNB_", 5) != 0) continue;
+        const char *eq = strchr(*e, '=');
+        const std::string name(*e, eq ? (size_t)(eq - *e) : strlen(*e));
+        bool known = false;
+        for (const KnobDef &d : g_knob_defs) known = known || name == d.name;
+        if (!known) {
+            err = "unknown environment switch " + name + " (include/dnn_b200.h lists the DNNB_* variables; unset it)";
+            return 1;
+        }
+    }
+    bool bad = false;
+    auto value = [&](const char *name, int dflt) -> int {
+        const KnobDef *def = nullptr;
+        for (const KnobDef &d : g_knob_defs)
+            if (strcmp(d.name, name) == 0) def = &d;
+        const char *v = getenv(name);
+        if (!v || !def) return dflt;
+        long x;
+        if (def->is_flag && v[0] == 0) x = 1;
+        else {
+            char *end = nullptr;
+            x = strtol(v, &end, 10);
+            if (end == v || *end != 0 || x < def->lo || x > def->hi) {
+                err = std::string("bad value for ") + name + ": '" + v + "'";
+                bad = true;
+                return dflt;
+            }
+        }
+        if ((int)x != dflt) {
+            if (!active.empty()) active += ",";
+            active += std::string(name) + "=" + std::to_string(x);
+        }
+        return (int)x;
+    };
+    k = Knobs();
+    k.latency = value("DNNB_LATENCY_MODE", 0) != 0;
+    k.no_pdl = value("DNNB_NO_PDL", 0) != 0;
+    k.no_graph = value("DNNB_NO_GRAPH", 0) != 0;
+    k.force_simt = value("DNNB_FORCE_SIMT", 0) != 0;
+    k.no_conv0 = value("DNNB_NO_CONV0", 0) != 0;
+    k.conv0_pack = value("DNNB_CONV0_PACK", 0) != 0;
+    k.no_rowpair = value("DNNB_NO_ROWPAIR", 0) != 0;
+    const int lin_on = getenv("DNNB_ROWPAIR_LINEAR") ? value("DNNB_ROWPAIR_LINEAR", -1) : -1;
+    k.rowpair_linear = lin_on >= 0 ? lin_on : (value("DNNB_NO_ROWPAIR_LINEAR", 0) != 0 ? 0 : -1);
+    k.rowpair_max_tr = value("DNNB_ROWPAIR_MAX_TR", 8);
+    k.no_pool_first = value("DNNB_NO_POOL_FIRST", 0) != 0;
+    k.no_stage_out = value("DNNB_NO_STAGE_OUT", 0) != 0;
+    k.no_mt2 = value("DNNB_NO_MT2", 0) != 0;
+    k.mt2_mask = getenv("DNNB_MT2_MASK") ? value("DNNB_MT2_MASK", -1) : -1;
+    k.no_pair = value("DNNB_NO_PAIR", 0) != 0;
+    k.pair_mt = value("DNNB_PAIR_MT", 1);
+    k.pair_min_tiles = getenv("DNNB_PAIR_MIN_TILES") ? value("DNNB_PAIR_MIN_TILES", -1) : -1;
+    k.pair_no_tail = value("DNNB_PAIR_NO_TAIL", 0) != 0;
+    k.no_pair_tail = value("DNNB_NO_PAIR_TAIL", 0) != 0;
+    k.no_tail = value("DNNB_NO_TAIL", 0) != 0;
+    k.lat_fuse_nb = value("DNNB_LAT_FUSE_NB", 0);
+    k.split_min_stages = value("DNNB_SPLIT_MIN_STAGES", 0);
+    k.no_u8_fusion = value("DNNB_NO_U8_FUSION", 0) != 0;
+    k.no_pool1_fusion = value("DNNB_NO_POOL1_FUSION", 0) != 0;
+    k.no_cluster_splitk = value("DNNB_NO_CLUSTER_SPLITK", 0) != 0;
+    k.no_tma_store = value("DNNB_NO_TMA_STORE", 0) != 0;
+    k.no_l2_prefetch = value("DNNB_NO_L2_PREFETCH", 0) != 0;
+    return bad ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -167,6 +237,8 @@ struct dnnb_net {
     // latency path (DNNB_LATENCY_MODE=1 at finalize): programmatic dependent launches, and the launch
     // sequence of dnnb_net_forward_device replayed from a CUDA graph per (input, output) pointer pair
     Knobs knobs;
+    std::string knobs_active;            // "NAME=value,..." of the DNNB_* switches that are not at their default
+    int latency_override = -1;           // dnnb_net_set_latency: -1 = DNNB_LATENCY_MODE decides
     bool pdl = false, use_graph = false;
     struct GraphSlot {
         const void *in = nullptr;
@@ -284,6 +356,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
     b.round_tf32 = net->precision == DNNB_TF32 && !last;
     b.family = DNNB_KERNEL_SIMT;
     b.pool_fused = false;
+    b.pool_separate = false;
+    // a block may be planned more than once (BF16 block 0): start from a clean plan every time
+    b.umma = nullptr; b.umma_tail = nullptr; b.pair = nullptr; b.pair_tail = nullptr; b.rowpair = nullptr;
+    b.rp_linear = false; b.op_bf16 = false;
+    b.grid = b.grid_tail = b.grid_pair_tail = 0;
     const Knobs &kn = net->knobs;
     const bool force_simt = kn.force_simt;
 

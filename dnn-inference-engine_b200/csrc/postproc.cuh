@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(kThreads) detect_kernel(const Params p) {
                 __syncwarp();
             }
             if (lane == 0) p.counts[img] = nk;
+            // rows past the kept boxes are defined too (zeros): the caller's buffer never sees stale device memory
+            for (int k = nk + lane; k < p.max_det; k += 32) p.dets[(size_t)img * p.max_det + k] = Det{};
         }
         __syncthreads();
     }

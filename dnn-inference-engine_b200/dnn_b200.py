@@ -34,11 +34,14 @@ F32_MIN = np.finfo(np.float32).min
 
 
 class DnnInferenceEngine(object):
-    def __init__(self, graph, debug=False, precision="tf32", device=0, latency=None):
+    def __init__(self, graph, debug=False, precision="tf32", device=0, latency=None, devices=None):
+        """devices=[0, 1, ...]: batch-sharded over several GPUs (sharded.MultiGpuEngine: contiguous slices of the
+        batch, weights replicated once per device, no collective; the result is assembled in one host array)."""
         self.g = graph
         self.debug = debug
         self.precision = precision
-        self.device = device
+        self.device = device if devices is None else list(devices)[0]
+        self.devices = None if devices is None else list(devices)
         self.latency = latency       # True: plan for single-image latency (see _lib.Net); None: DNNB_LATENCY_MODE decides
         self.save_dir = os.path.join(os.getcwd(), "intermediate")
         self._net = None
@@ -91,7 +94,7 @@ class DnnInferenceEngine(object):
             blocks.append(blk)
         return blocks
 
-    def _build_net(self, blocks):
+    def _build_net(self, blocks, device=None, batch=None):
         spec = []
         for blk in blocks:
             conv, bn, pool = blk["conv"], blk.get("bn"), blk.get("pool")
@@ -103,7 +106,15 @@ class DnnInferenceEngine(object):
                 "leaky": "leaky" in blk,
                 "pool": None if pool is None else (pool.ksize[1], pool.strides[1], pool.padding),
             })
-        return _lib.Net(self.g.in_node.in_shape, spec, precision=self.precision, device=self.device, latency=self.latency)
+        in_shape = list(self.g.in_node.in_shape)
+        if batch is not None:
+            in_shape[0] = batch
+        return _lib.Net(in_shape, spec, precision=self.precision, device=self.device if device is None else device,
+                        latency=self.latency)
+
+    def _build_sharded(self, blocks):
+        import sharded
+        return sharded.MultiGpuEngine(lambda dev, n: self._build_net(blocks, dev, n), self.g.in_node.in_shape[0], self.devices)
 
     def run(self, tin):
         self.g.in_node.set_input(tin)
@@ -111,9 +122,9 @@ class DnnInferenceEngine(object):
             blocks = self._fuse()
             if blocks is not None:
                 if self._net is None:
-                    self._net = self._build_net(blocks)
+                    self._net = self._build_sharded(blocks) if self.devices else self._build_net(blocks)
                     self.fused_blocks = [b["nodes"] for b in blocks]
-                out = self._net.forward(tin)
+                out = self._net.run(f32c(tin)) if self.devices else self._net.forward(tin)
                 self.g.out_node.result = out
                 return out
         # node-by-node (debug mode, or a graph that is not a chain of conv blocks)
@@ -135,12 +146,17 @@ class DnnInferenceEngine(object):
         block granularity (the tensors inside a fused block never exist)."""
         if self._net is None:
             raise RuntimeError("no fused run yet")
+        if self.devices:
+            raise RuntimeError("block results are kept per device: run on one device to compare layers")
         return {nodes[-1]: self._net.block_output(i) for i, nodes in enumerate(self.fused_blocks)}
 
     def kernel_plan(self):
         if self._net is None:
-            self._net = self._build_net(self._fuse())
-        return [self._net.block_info(i) for i in range(self._net.num_blocks)]
+            blocks = self._fuse()
+            self._net = self._build_sharded(blocks) if self.devices else self._build_net(blocks)
+            self.fused_blocks = [b["nodes"] for b in blocks]
+        net = next(n for n in self._net.nets if n is not None) if self.devices else self._net
+        return [net.block_info(i) for i in range(net.num_blocks)]
 
     def close(self):
         if self._net is not None:

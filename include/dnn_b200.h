@@ -95,8 +95,23 @@ int dnnb_net_add_block(dnnb_net *net, const float *kernel, int kh, int kw, int i
  * CTAs (deterministic, but a different fp32 summation order than the default plan), kernels chained by
  * programmatic dependent launch, and dnnb_net_forward_device replayed from a CUDA graph per
  * (dev_in, dev_out) pair from the second call on (the first call launches directly and sets function
- * attributes and tensor maps).  DNNB_NO_PDL / DNNB_NO_GRAPH switch the last two off. */
+ * attributes and tensor maps).  DNNB_NO_PDL / DNNB_NO_GRAPH switch the last two off.
+ * Streams: the *_async host calls pipeline on three streams owned by the network.  The device-entry calls run on
+ * the caller's stream (or the network's own when NULL); those of them that use the network's own staging /
+ * result buffers (dev_out == NULL, uint8 input that needs a preprocessing pass, dnnb_net_detect_device) order
+ * themselves after the host pipeline's copies on those buffers and are in turn waited for by later *_async calls. */
 int dnnb_net_finalize(dnnb_net *net);
+
+/* Selects the small-batch latency plan for this network without touching the environment: 1 = on, 0 = off,
+ * -1 = DNNB_LATENCY_MODE decides (the default).  Call before dnnb_net_finalize. */
+int dnnb_net_set_latency(dnnb_net *net, int mode);
+
+/* Environment switches.  dnnb_net_finalize reads the DNNB_* variables (DESIGN.md section 4c lists them; apart
+ * from DNNB_LATENCY_MODE they force a particular kernel for tests and ablation measurements) and FAILS on a
+ * DNNB_* name it does not know or a value it cannot parse, so that a stale variable in a shell cannot silently
+ * change the plan.  dnnb_net_knobs writes the switches that are not at their default as "NAME=value,..." (an
+ * empty string for the default plan) into buf. */
+int dnnb_net_knobs(dnnb_net *net, char *buf, int buf_len);
 
 int dnnb_net_num_blocks(dnnb_net *net, int *n);
 int dnnb_net_out_shape(dnnb_net *net, int *b, int *h, int *w, int *c);
@@ -105,7 +120,7 @@ int dnnb_net_out_shape(dnnb_net *net, int *b, int *h, int *w, int *c);
 int dnnb_net_forward(dnnb_net *net, const float *host_in, float *host_out);
 
 /* Device in / device out (float32 NHWC in HBM), asynchronous on `stream` (a cudaStream_t, or
- * NULL for the network's own stream).  dev_out may be NULL: the result then stays in the
+ * NULL for the network's own stream).  Both pointers must be 16-byte aligned.  dev_out may be NULL: the result then stays in the
  * network's last activation buffer (see dnnb_net_block_output_ptr). */
 int dnnb_net_forward_device(dnnb_net *net, const void *dev_in, void *dev_out, void *stream);
 
@@ -132,8 +147,15 @@ int dnnb_net_forward_frames_async(dnnb_net *net, const unsigned char *host_frame
 int dnnb_resize_input(int device, const unsigned char *frames_host, int batch, int src_h, int src_w,
                       int dst_h, int dst_w, int bgr, float *out_host);
 
-/* Waits for everything queued on the network's own stream. */
+/* Waits for everything queued on the network's own streams. */
 int dnnb_net_sync(dnnb_net *net);
+
+/* Streaming: the *_async host calls alternate between two pipeline slots (device-side input / output buffers).
+ * dnnb_net_next_slot tells which slot the NEXT *_async call will use; dnnb_net_wait_slot returns once the
+ * results of the most recent job of `slot` are in the caller's host buffers -- so a loop can wait for job k - 1
+ * while job k runs (streaming.StreamingDetector; the frame loop of proj1/__init__.py:71-137). */
+int dnnb_net_next_slot(dnnb_net *net, int *slot);
+int dnnb_net_wait_slot(dnnb_net *net, int slot);
 
 /* Debug / layer-wise comparison: copies block `block`'s output (after its pool, if any) to
  * host as float32 [b,h,w,c]; shape via dnnb_net_block_info. */

@@ -239,6 +239,14 @@ def test_yolo_block_outputs_layerwise_against_oracle(oracle_libs):
         ref = nodes[ends[blk]]
         assert res.shape == ref.shape
         assert normalised_error(res, ref) < 5e-3, "block %d" % blk
+    # the same through layer_compare.compare_blocks: goldens on disk in the proj1 numbering (layer_0 = conv2d_0)
+    import layer_compare, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for i, t in enumerate(nodes[1:]):
+            np.save(os.path.join(d, "layer_%d.npy" % i), t)
+        rows = layer_compare.compare_blocks(eng, d, quiet=True)
+    assert [r["index"] for r in rows] == [e - 1 for e in ends] and rows[0]["name"] == "max_pool2d_0"
+    assert max(r["normalised"] for r in rows) < 5e-3
     eng.close()
 
 
@@ -351,6 +359,64 @@ def test_batch_sharding_over_two_gpus_equals_one_gpu():
     out = eng.run(hin.array, hout.array)
     np.testing.assert_array_equal(out, ref)
     eng.close(); one.close(); hin.free(); hout.free()
+
+
+def test_sharded_engine_through_the_drop_in_api_on_one_device():
+    """DnnInferenceEngine(devices=[...]) is the batch-sharded driver behind the reference's API.  With the same
+    device listed twice the whole sharded path (ragged slices, one resident network per slice, async forwards,
+    result assembled in one host array) runs on a 1-GPU box; slices must land where a single network puts them."""
+    weights = make_weights(0)
+    x = make_images(5, seed=410)
+    g = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g, list(x.shape), weights)
+    one = dnn_b200.DnnInferenceEngine(g, False, precision="tf32", device=0)
+    ref = one.run(x).copy()
+    one.close()
+    g2 = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g2, list(x.shape), weights)
+    eng = dnn_b200.DnnInferenceEngine(g2, False, precision="tf32", devices=[0, 0])
+    out = eng.run(x)
+    assert [n.in_shape[0] for n in eng._net.nets] == [3, 2]
+    np.testing.assert_array_equal(out, ref)
+    assert g2.out_node.result is out
+    assert all(p["kernel"].startswith("umma") for p in eng.kernel_plan())
+    eng.close()
+
+
+def test_async_entry_points_reject_buffers_they_would_overrun():
+    spec = [{"kernel": np.zeros((3, 3, 3, 16), np.float32), "padding": "SAME", "biases": np.zeros(16, np.float32)}]
+    net = _lib.Net((2, 16, 16, 3), spec, precision="tf32", device=0)
+    out = np.zeros(net.out_shape, np.float32)
+    with pytest.raises(TypeError):
+        net.forward_async(np.zeros((2, 16, 16, 3), np.float64), out)
+    with pytest.raises(ValueError):
+        net.forward_async(np.zeros((4, 16, 16, 3), np.float32)[::2], out)
+    with pytest.raises(ValueError):
+        net.forward_async(np.zeros((2, 16, 16, 3), np.float32), np.zeros((1,) + net.out_shape[1:], np.float32))
+    with pytest.raises(TypeError):
+        net.forward_u8_async(np.zeros((2, 16, 16, 3), np.float32), out)
+    net.close()
+
+
+def test_unknown_environment_switch_fails_finalize(monkeypatch):
+    spec = [{"kernel": np.zeros((3, 3, 3, 16), np.float32), "padding": "SAME", "biases": np.zeros(16, np.float32)}]
+    monkeypatch.setenv("DNNB_NO_PIAR", "1")                       # a typo must not silently run the default plan
+    with pytest.raises(RuntimeError, match="unknown environment switch DNNB_NO_PIAR"):
+        _lib.Net((1, 16, 16, 3), spec)
+    monkeypatch.delenv("DNNB_NO_PIAR")
+    monkeypatch.setenv("DNNB_PAIR_MT", "three")
+    with pytest.raises(RuntimeError, match="bad value for DNNB_PAIR_MT"):
+        _lib.Net((1, 16, 16, 3), spec)
+    monkeypatch.delenv("DNNB_PAIR_MT")
+    monkeypatch.setenv("DNNB_NO_PAIR", "1")
+    monkeypatch.setenv("DNNB_PAIR_MIN_TILES", "1")
+    net = _lib.Net((1, 16, 16, 3), spec, latency=True)
+    assert net.knobs() == {"DNNB_NO_PAIR": "1", "DNNB_PAIR_MIN_TILES": "1", "set_latency": "1"}
+    net.close()
+    monkeypatch.delenv("DNNB_NO_PAIR"); monkeypatch.delenv("DNNB_PAIR_MIN_TILES")
+    net = _lib.Net((1, 16, 16, 3), spec)
+    assert net.knobs() == {}
+    net.close()
 
 
 def test_valid_padding_and_odd_pool_take_the_cuda_core_path(oracle_libs):
@@ -522,6 +588,13 @@ def test_debug_mode_runs_node_by_node_and_dumps_layers(tmp_path, monkeypatch):
         got = np.load(tmp_path / "intermediate" / ("layer_%d.npy" % i))
         np.testing.assert_allclose(got, gold["node_%02d" % i], rtol=1e-5, atol=1e-5, err_msg="layer %d" % i)
     np.testing.assert_allclose(out, gold["node_%02d" % (n_nodes - 1)], rtol=1e-5, atol=1e-5)
+    # the reference's own way of checking the dump: npc_cmp_print against a directory of golden layer_N.npy
+    import layer_compare
+    os.makedirs(tmp_path / "golden")
+    for i in range(n_nodes):
+        np.save(tmp_path / "golden" / ("layer_%d.npy" % i), gold["node_%02d" % i])
+    rows = layer_compare.compare_dirs(str(tmp_path / "intermediate"), str(tmp_path / "golden"), quiet=True)
+    assert len(rows) == n_nodes and max(r["normalised"] for r in rows) < 1e-5
     # the same graph, fused (small odd shapes -> CUDA-core kernels + separate pools): same answer
     fused = dnn_b200.DnnInferenceEngine(g, False, precision="fp32").run(x)
     np.testing.assert_allclose(fused, out, rtol=1e-4, atol=1e-4)
