@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "epilogue_pool1.cuh"
 #include "ptx.cuh"
 
 namespace pairconv {
@@ -39,6 +40,8 @@ struct Params {
     int num_n_tiles;
     int M_total;              // B * H * W
     int m_base;               // first output pixel of this launch
+    int m_stride;             // output pixels each CTA's 128 rows advance: 128, or 128 - (W + 1) with the fused 2x2/1 pool
+    float *prepool;           // POOL1 debug: also dump the pooled-over activations [B,H,W,OC] fp32
     const float *scale;
     const float *shift;
     void *out;
@@ -47,12 +50,12 @@ struct Params {
 
 // kBN = output channels per pair tile (256; 128 for the tail launch over a block's last rows, so that
 // they spread over twice as many pairs)
-template <int MT, int kBN = 256>
+template <int MT, int kBN = 256, bool POOL1 = false>
 struct Cfg {
     static constexpr int A_TILE = kBM * kSwz;
     static constexpr int B_HALF = (kBN / 2) * kSwz;
     static constexpr int STAGE_BYTES = MT * A_TILE + B_HALF;
-    static constexpr int TAIL_BYTES = 1024 + 2 * 1024 * 4;
+    static constexpr int TAIL_BYTES = 1024 + 2 * 1024 * 4 + (POOL1 ? pool1::kStageBytes : 0);
     static constexpr int STAGES_RAW = (227 * 1024 - 1024 - TAIL_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES + 1024;
@@ -62,10 +65,10 @@ struct Cfg {
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM allocation");
 };
 
-template <bool BF16, bool OUT_BF16, int MT, int kBN = 256>
+template <bool BF16, bool OUT_BF16, int MT, int kBN = 256, bool POOL1 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-    using C = Cfg<MT, kBN>;
+    using C = Cfg<MT, kBN, POOL1>;
     constexpr int STAGES = C::STAGES;
     constexpr int ACC = C::ACC_STAGES;
     constexpr int ES = BF16 ? 2 : 4;
@@ -78,6 +81,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
     float *s_scale = reinterpret_cast<float *>(tail + 1024);
     float *s_shift = s_scale + 1024;
+    float *s_stage = s_shift + 1024;      // POOL1: [128][33] staging of one column chunk
 
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t bar_full = ptx::smem_u32(bars);
@@ -126,7 +130,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 int w0[MT], h0[MT], n0[MT];
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
-                    const int m0 = p.m_base + ((m_tile * MT + i) * 2 + (int)rank) * kBM;
+                    const int m0 = p.m_base + ((m_tile * MT + i) * 2 + (int)rank) * p.m_stride;
                     n0[i] = m0 / (p.H * p.W);
                     const int rem = m0 - n0[i] * (p.H * p.W);
                     h0[i] = rem / p.W;
@@ -196,7 +200,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int mi = 0; mi < MT; ++mi) {
-                const int m = p.m_base + ((m_tile * MT + mi) * 2 + (int)rank) * kBM + row;
+                const int m_first = p.m_base + ((m_tile * MT + mi) * 2 + (int)rank) * p.m_stride;
+                const int m = m_first + row;
                 const bool valid = m < p.M_total;
 #pragma unroll 1
                 for (int chunk = 0; chunk < kBN / 32; ++chunk) {
@@ -217,6 +222,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (p.leaky) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                    }
+                    if constexpr (POOL1) {
+                        if constexpr (OUT_BF16) {       // the reference pools the stored values: round first
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                        } else if (p.round_tf32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+                        }
+                        pool1::dump_prepool(v, m, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
+                        pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_stage), v, quarter, lane, m_first, p.m_stride, p.M_total, p.H,
+                                                     p.OC, col0, p.out, p.prepool);
+                        continue;
                     }
                     if (!valid) continue;
                     if constexpr (OUT_BF16) {

@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "epilogue_pool1.cuh"
 #include "ptx.cuh"
 
 namespace umma_conv {
@@ -45,6 +46,8 @@ struct Params {
     int M_total;          // im2col mode: B*H*W
     int m_base;           // im2col mode: first output pixel of this launch (a block may be cut into a main launch
                           // of whole waves and a finer-tiled tail launch over the remaining rows)
+    int m_stride;         // im2col mode: output pixels a 128-row tile advances: 128, or 128 - (W + 1) when the 2x2/1
+                          // SAME pool is fused (POOL1: the last W + 1 rows of a tile are halo, epilogue_pool1.cuh)
     const float *scale;   // [num_n_tiles*BN]  gamma / sqrt(var + eps)      (1 when no BN)
     const float *shift;   // [num_n_tiles*BN]  (bias - mean) * scale         (bias when no BN)
     void *out;            // [B, OH, OW, OC]
@@ -72,12 +75,12 @@ struct Params {
 // STAGE_OUT reserves 4 x 32 rows x BN floats so that a tile whose rows are narrower than a 16-byte
 // multiple (block 8: 125 channels = 500-byte rows) is staged in shared memory and written as one
 // contiguous, coalesced run instead of 4-byte scattered stores.
-template <int BN, int SWZ, int KBS, int MT = 1, bool STAGE_OUT = false>
+template <int BN, int SWZ, int KBS, int MT = 1, bool STAGE_OUT = false, bool POOL1 = false>
 struct Cfg {
     static constexpr int A_TILE = kBM * SWZ;
     static constexpr int B_TILE = BN * SWZ;
     static constexpr int STAGE_BYTES = KBS * (MT * A_TILE + B_TILE);
-    static constexpr int OUT_STAGE_BYTES = STAGE_OUT ? kBM * BN * 4 : 0;
+    static constexpr int OUT_STAGE_BYTES = STAGE_OUT ? kBM * BN * 4 : POOL1 ? pool1::kStageBytes : 0;
     static constexpr int TAIL_BYTES = 1024 /*barriers+tmem slot*/ + 2 * 1024 * 4 /*scale, shift*/ + OUT_STAGE_BYTES;
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/;
     static constexpr int STAGES_RAW = (SMEM_BUDGET - TAIL_BYTES) / STAGE_BYTES;
@@ -91,12 +94,14 @@ struct Cfg {
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocations are powers of two");
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1, bool STAGE_OUT = false>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1, bool STAGE_OUT = false,
+          bool POOL1 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const Params p) {
-    using C = Cfg<BN, SWZ, KBS, MT, STAGE_OUT>;
+    using C = Cfg<BN, SWZ, KBS, MT, STAGE_OUT, POOL1>;
     static_assert(!STAGE_OUT || (IM2COL && !POOL && !OUT_BF16 && MT == 1), "staged output: plain fp32 im2col tiles only");
+    static_assert(!POOL1 || (IM2COL && !POOL && !STAGE_OUT), "the fused 2x2/1 pool needs im2col tiles");
     constexpr int STAGES = C::STAGES;
     constexpr int ACC = C::ACC_STAGES;
     constexpr int ES = BF16 ? 2 : 4;
@@ -111,7 +116,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 512);
     float *s_scale = reinterpret_cast<float *>(tail + 1024);
     float *s_shift = s_scale + 1024;
-    float *s_out = s_shift + 1024;       // STAGE_OUT only: [4 warps][32 rows][OC]
+    float *s_out = s_shift + 1024;       // STAGE_OUT: [4 warps][32 rows][OC]; POOL1: [128][33] staging of one column chunk
 
     const uint32_t smem_base = ptx::smem_u32(smem);
     const uint32_t bar_full = ptx::smem_u32(bars);
@@ -201,7 +206,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if constexpr (IM2COL) {
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        const int m0 = p.m_base + (m_tile * MT + i) * kBM;
+                        const int m0 = p.m_base + (m_tile * MT + i) * p.m_stride;
                         n0[i] = m0 / (p.H * p.W);
                         const int rem = m0 - n0[i] * (p.H * p.W);
                         h0[i] = rem / p.W;
@@ -417,7 +422,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 size_t out_pix;   // index of the stored pixel (pooled pixel when POOL)
                 size_t pre_pix = 0;   // index of the conv pixel (debug pre-pool dump)
                 if constexpr (IM2COL) {
-                    const int m = p.m_base + (m_tile * MT + mi) * kBM + row;
+                    const int m = p.m_base + (m_tile * MT + mi) * p.m_stride + row;
                     valid = m < p.M_total;
                     out_pix = (size_t)m;
                 } else {
@@ -464,7 +469,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
                     }
 
-                    if constexpr (POOL) {
+                    if constexpr (POOL1) {
+                        pool1::dump_prepool(v, (int)out_pix, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
+                        pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
+                                                     p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool);
+                    } else if constexpr (POOL) {
                         if (p.prepool != nullptr && valid) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
@@ -557,7 +566,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if constexpr (STAGE_OUT) {
                     // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
                     __syncwarp();
-                    const int row0 = p.m_base + m_tile * kBM + quarter * 32;
+                    const int row0 = p.m_base + m_tile * p.m_stride + quarter * 32;
                     const int rows = min(32, p.M_total - row0);
                     if (rows > 0) {
                         const int count = rows * p.OC;

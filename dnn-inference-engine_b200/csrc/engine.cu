@@ -124,11 +124,11 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         p.workspace = b.d_workspace; p.counters = b.d_counters;
         if (b.pair) {
             pairconv::Params q = b.pp;
-            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out;
+            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
             if (q.num_m_tiles > 0) CK(b.pair->launch(b.map_a, b.map_b_pair, q, b.grid, st));
             if (b.pair_tail) {
                 pairconv::Params t = b.pp_tail;
-                t.scale = b.d_scale; t.shift = b.d_shift; t.out = conv_out;
+                t.scale = b.d_scale; t.shift = b.d_shift; t.out = conv_out; t.prepool = prepool;
                 CK(b.pair_tail->launch(b.map_a, b.map_b_pair_tail, t, b.grid_pair_tail, st));
             }
         } else {

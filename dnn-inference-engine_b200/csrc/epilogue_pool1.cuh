@@ -1,0 +1,89 @@
+// epilogue_pool1.cuh -- the 2x2 stride-1 SAME max-pool of block 5 (max_pool2d_5, proj3/yolov2tiny.py:64:
+// ksize 2, stride 1 on 13x13 -> pad 0 top/left, 1 bottom/right with finfo(float32).min,
+// proj3/dnn_openblas.py:232-235) fused into the epilogue of the im2col kernels.
+//
+// An im2col tile is 128 CONSECUTIVE output pixels m = (n*H + h)*W + w, so the window of pixel m is rows
+// m, m+1, m+W, m+W+1 of the same tile as long as m+W+1 is inside it: tiles advance by 128 - (W+1) rows
+// (`m_stride`) and the last W+1 rows of every tile are halo, recomputed by the next tile.  Per 32-column
+// chunk the four epilogue warps park their activated rows in a [128][36]-float staging area (16-byte
+// stores, conflict-free; reads with lane = channel are conflict-free too), then warp q emits output rows
+// 32q .. 32q+31: it loads its 32 + W + 1 staged rows once, all loads in flight together, takes the
+// horizontal pair maxima p[r] = max(s[r], s[r+1]) and the vertical ones max(p[r], p[r+W]) in registers, and
+// stores one 128-byte line per row.  Neighbours outside the image are skipped, which is what the reference's
+// -FLT_MAX padding amounts to; max() does not depend on the (di, dj) order the reference visits
+// (dnn_openblas.c:209-222).  The image width is a compile-time constant (13: the YOLOv2-tiny grid) so that
+// the whole window walk unrolls; the planner keeps the separate pool kernel for any other width.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+
+namespace pool1 {
+
+constexpr int kW = 13;                           // image width the fused form is compiled for
+constexpr int kHalo = kW + 1;
+constexpr int kPitch = 36;                       // floats per staged row (144 bytes: 16-byte aligned rows)
+constexpr int kStageBytes = 128 * kPitch * 4;
+
+__device__ __forceinline__ float lds(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// v: columns [col0, col0 + 32) of tile row 32 * quarter + lane, activated and rounded to the storage type.
+// m0: output pixel of tile row 0.  Rows [0, m_stride) of the tile are stored; all 128 epilogue threads call
+// this together (two named-barrier syncs).  prepool (debug): also dump the pooled-over activations [B,H,W,OC] fp32.
+template <bool OUT_BF16>
+__device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[32], int quarter, int lane, int m0,
+                                            int m_stride, int M_total, int H, int OC, int col0, void *out,
+                                            float *prepool) {
+    const uint32_t mine = s_stage + (uint32_t)(quarter * 32 + lane) * (kPitch * 4);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) sts4(mine + 4 * j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int r0 = quarter * 32;
+    // staged rows r0 .. r0 + 32 + kW + 1 of this lane's channel (rows past the tile are never used: clamp the address)
+    constexpr int kRows = 32 + kHalo + 1;
+    float x[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) x[i] = lds(s_stage + (uint32_t)(min(r0 + i, 127) * kPitch + lane) * 4);
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // everybody has its rows: the staging area may be rewritten
+    const int m = m0 + r0;
+    const int hw = m % (H * kW);
+    int h = hw / kW, w = hw - h * kW;
+    // horizontal pair maxima; row i and row i + kW are the same image column, so one walk over w serves both
+    int wi = w;
+#pragma unroll
+    for (int i = 0; i < 32 + kW; ++i) {
+        if (wi + 1 < kW) x[i] = fmaxf(x[i], x[i + 1]);
+        if (++wi == kW) wi = 0;
+    }
+    const int col = col0 + lane;
+    if (col >= OC) return;
+    const int n_rows = min(min(32, m_stride - r0), M_total - m);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i < n_rows) {
+            // the debug dump wants the un-pooled value: it was overwritten above only when it had a right neighbour
+            const float a = (h + 1 < H) ? fmaxf(x[i], x[i + kW]) : x[i];
+            if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[(size_t)(m + i) * OC + col] = __float2bfloat16_rn(a);
+            else static_cast<float *>(out)[(size_t)(m + i) * OC + col] = a;
+        }
+        if (++w == kW) { w = 0; if (++h == H) h = 0; }
+    }
+    (void)prepool;
+}
+
+// Debug variant of the first half: dumps this thread's own row of the chunk (all 128 tile rows are written by
+// somebody: rows [0, m_stride) belong to this tile, the halo rows to the next one, which writes the same values).
+__device__ __forceinline__ void dump_prepool(const float (&v)[32], int m, int M_total, int owned, int OC, int col0,
+                                             float *prepool) {
+    if (prepool == nullptr || !owned || m >= M_total) return;
+    for (int j = 0; j < 32; ++j)
+        if (col0 + j < OC) prepool[(size_t)m * OC + col0 + j] = v[j];
+}
+
+}  // namespace pool1

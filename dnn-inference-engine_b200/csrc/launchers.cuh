@@ -55,6 +55,7 @@ struct UmmaKey {
     bool im2col, pool;
     int mt;   // 128-row M tiles per CTA tile
     bool stage_out;   // output tile staged in smem (rows that are not 16-byte multiples)
+    bool pool1 = false;   // 2x2/1 SAME max-pool fused in the epilogue (im2col tiles overlapping by W + 1 rows)
 };
 struct UmmaEntry {
     UmmaKey key;
@@ -62,11 +63,11 @@ struct UmmaEntry {
     int stages, smem;
 };
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false>
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false>
 cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
                         cudaStream_t st) {
-    using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO>;
-    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO>;
+    using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO, P1>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
@@ -80,6 +81,9 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
 #define UMMA_ENTRY_SO(BF16, BN, SWZ, KBS)                                                                  \
     {{BF16, false, BN, SWZ, KBS, true, false, 1, true}, &launch_umma<BF16, false, BN, SWZ, KBS, true, false, 1, true>, \
      umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES}
+#define UMMA_ENTRY_P1(BF16, OBF, BN)                                                                       \
+    {{BF16, OBF, BN, 128, 1, true, false, 1, false, true}, &launch_umma<BF16, OBF, BN, 128, 1, true, false, 1, false, true>, \
+     umma_conv::Cfg<BN, 128, 1, 1, false, true>::STAGES, umma_conv::Cfg<BN, 128, 1, 1, false, true>::SMEM_BYTES}
 #define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
 
 const UmmaEntry g_umma_table[] = {
@@ -122,13 +126,17 @@ const UmmaEntry g_umma_table[] = {
     // output staged through smem: the 125-channel head (block 8)
     UMMA_ENTRY_SO(false, 128, 128, 1),
     UMMA_ENTRY_SO(true, 128, 128, 1),
+    // 2x2/1 SAME pool fused (block 5): whole block at small batches (BN 256), tail rows behind the CTA pairs (BN 128)
+    UMMA_ENTRY_P1(false, false, 256), UMMA_ENTRY_P1(false, false, 128),
+    UMMA_ENTRY_P1(true, true, 256),   UMMA_ENTRY_P1(true, true, 128),
+    UMMA_ENTRY_P1(true, false, 256),  UMMA_ENTRY_P1(true, false, 128),
 };
 
 const UmmaEntry *find_umma(const UmmaKey &k) {
     for (const UmmaEntry &e : g_umma_table)
         if (e.key.bf16 == k.bf16 && e.key.out_bf16 == k.out_bf16 && e.key.bn == k.bn && e.key.swz == k.swz &&
             e.key.kbs == k.kbs && e.key.im2col == k.im2col && e.key.pool == k.pool && e.key.mt == k.mt &&
-            e.key.stage_out == k.stage_out)
+            e.key.stage_out == k.stage_out && e.key.pool1 == k.pool1)
             return &e;
     return nullptr;
 }
@@ -142,26 +150,32 @@ struct PairEntry {
     int mt, bn;
     PairLauncher launch;
     int stages;
+    bool pool1;
 };
-template <bool BF16, bool OUT_BF16, int MT, int BN>
+template <bool BF16, bool OUT_BF16, int MT, int BN, bool P1 = false>
 cudaError_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const pairconv::Params &p, int grid, cudaStream_t st) {
-    using C = pairconv::Cfg<MT, BN>;
-    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT, BN>;
+    using C = pairconv::Cfg<MT, BN, P1>;
+    auto kern = pairconv::conv_pair_kernel<BF16, OUT_BF16, MT, BN, P1>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
     kern<<<grid, pairconv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
     return cudaGetLastError();
 }
-#define PAIR_ENTRY(BF16, OBF, MT, BN) {BF16, OBF, MT, BN, &launch_pair<BF16, OBF, MT, BN>, pairconv::Cfg<MT, BN>::STAGES}
+#define PAIR_ENTRY(BF16, OBF, MT, BN) {BF16, OBF, MT, BN, &launch_pair<BF16, OBF, MT, BN>, pairconv::Cfg<MT, BN>::STAGES, false}
+#define PAIR_ENTRY_P1(BF16, OBF, BN) {BF16, OBF, 1, BN, &launch_pair<BF16, OBF, 1, BN, true>, pairconv::Cfg<1, BN, true>::STAGES, true}
 const PairEntry g_pair_table[] = {
     PAIR_ENTRY(false, false, 1, 256), PAIR_ENTRY(false, false, 2, 256), PAIR_ENTRY(false, false, 1, 128),
     PAIR_ENTRY(true, true, 1, 256),   PAIR_ENTRY(true, true, 2, 256),   PAIR_ENTRY(true, true, 1, 128),
     PAIR_ENTRY(true, false, 1, 256),  PAIR_ENTRY(true, false, 2, 256),  PAIR_ENTRY(true, false, 1, 128),
+    // fused 2x2/1 SAME pool (block 5)
+    PAIR_ENTRY_P1(false, false, 256), PAIR_ENTRY_P1(false, false, 128),
+    PAIR_ENTRY_P1(true, true, 256),   PAIR_ENTRY_P1(true, true, 128),
+    PAIR_ENTRY_P1(true, false, 256),  PAIR_ENTRY_P1(true, false, 128),
 };
-const PairEntry *find_pair(bool bf16, bool out_bf16, int mt, int bn = 256) {
+const PairEntry *find_pair(bool bf16, bool out_bf16, int mt, int bn = 256, bool pool1 = false) {
     for (const PairEntry &e : g_pair_table)
-        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt && e.bn == bn) return &e;
+        if (e.bf16 == bf16 && e.out_bf16 == out_bf16 && e.mt == mt && e.bn == bn && e.pool1 == pool1) return &e;
     return nullptr;
 }
 

@@ -451,8 +451,19 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
                 if (fuse && net->B * 2 <= nb && nb > kn.lat_fuse_nb && kn.latency) fuse = false;
             }
-            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false};
+            // the 2x2 stride-1 SAME pool of block 5 fused into the im2col epilogue: tiles advance by 128 - (W + 1)
+            // output pixels, the last W + 1 rows of each tile are halo (epilogue_pool1.cuh).  Not with split-K.
+            bool fuse1 = !fuse && b.pool_k == 2 && b.pool_s == 1 && b.pool_same && b.oh == b.ch && b.ow == b.cw &&
+                         b.ppt == 0 && b.ppl == 0 && b.iw == pool1::kW && swz == 128 && kbs == 1 && b.oc % 4 == 0 &&
+                         !kn.no_pool1_fusion && !kn.latency;
+            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false, fuse1};
             const UmmaEntry *e = find_umma(key);
+            if (!e && fuse1) {
+                fuse1 = false;
+                key.pool1 = false;
+                e = find_umma(key);
+            }
+            const int stride = fuse1 ? umma_conv::kBM - (b.iw + 1) : umma_conv::kBM;
             if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out) {
                 UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
                 key_so.stage_out = true;
@@ -460,7 +471,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 if (e_so) e = e_so;
             }
             int mt = 1;
-            if (e && !kn.no_mt2) {
+            if (e && !kn.no_mt2 && !fuse1) {
                 // 256-row CTA tiles (two M tiles share each weight tile) when there is enough work for
                 // at least two waves of them; DNNB_MT2_MASK (bit i = block i) overrides per block
                 const long m_rows = fuse ? (long)((net->B + nb - 1) / nb) * nb * b.ih * b.iw : (long)net->B * b.ih * b.iw;
@@ -481,7 +492,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
             if (e) {
                 b.umma = e;
                 b.family = fuse ? DNNB_KERNEL_UMMA_TILED : DNNB_KERNEL_UMMA_IM2COL;
-                b.pool_fused = fuse;
+                b.pool_fused = fuse || fuse1;
                 b.bn = bn;
                 b.swz = swz;
                 umma_conv::Params &p = b.up;
@@ -498,9 +509,10 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 } else {
                     p.tw = p.th = p.nb = 1;
                     p.M_total = net->B * b.ih * b.iw;
-                    p.num_m_tiles = (p.M_total + umma_conv::kBM * mt - 1) / (umma_conv::kBM * mt);
+                    p.num_m_tiles = (p.M_total + stride * mt - 1) / (stride * mt);
                     p.OH = b.ih; p.OW = b.iw;
                 }
+                p.m_stride = stride;
                 p.leaky = b.leaky;
                 p.round_tf32 = b.round_tf32;
                 // split-K when the output tiles alone cannot occupy the SMs (small batches)
@@ -530,12 +542,12 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                     // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
                     // MT = 2 everywhere 82.8 k, no pairs 82.5 k -- two accumulator stages and six smem stages are
                     // worth more than the last quarter of traffic
-                    const int pmt = kn.pair_mt;
-                    const PairEntry *pe = find_pair(in_bf16, b.out_bf16, pmt);
-                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false};
+                    const int pmt = fuse1 ? 1 : kn.pair_mt;
+                    const PairEntry *pe = find_pair(in_bf16, b.out_bf16, pmt, 256, fuse1);
+                    UmmaKey kt{in_bf16, b.out_bf16, 128, swz, kbs, true, false, 1, false, fuse1};
                     const UmmaEntry *et = find_umma(kt);
                     const int pairs = sms / 2;
-                    const int rows_per = 2 * pmt * umma_conv::kBM;
+                    const int rows_per = 2 * pmt * stride;
                     const int m_all = p.M_total / rows_per;                 // whole pair tiles
                     const int tiles_p = m_all * p.num_n_tiles;
                     const int min_tiles = kn.pair_min_tiles >= 0 ? kn.pair_min_tiles : 2 * pairs;
@@ -550,7 +562,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         q.KH = b.kh; q.KW = b.kw; q.PT = b.pt; q.PL = b.pl;
                         q.c_chunks = c_chunks;
                         q.num_m_tiles = main_m; q.num_n_tiles = p.num_n_tiles;
-                        q.M_total = p.M_total; q.m_base = 0;
+                        q.M_total = p.M_total; q.m_base = 0; q.m_stride = stride;
                         q.leaky = b.leaky; q.round_tf32 = b.round_tf32;
                         const int t = main_m * p.num_n_tiles;
                         b.grid = 2 * (t < pairs ? t : pairs);
@@ -558,8 +570,8 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         // whole pair tiles past the full waves: pairs again, in 256 x 128 tiles so that they
                         // spread over twice as many pairs (block 7: 20 tiles -> 40 of the 74 pairs, 100 -> 50 us)
                         b.pair_tail = nullptr;
-                        const PairEntry *pt = pmt == 1 ? find_pair(in_bf16, b.out_bf16, 1, 128) : nullptr;
-                        const int m_pt = (p.M_total - rows_done) / (2 * umma_conv::kBM);
+                        const PairEntry *pt = pmt == 1 ? find_pair(in_bf16, b.out_bf16, 1, 128, fuse1) : nullptr;
+                        const int m_pt = (p.M_total - rows_done) / (2 * stride);
                         if (pt && m_pt > 0 && !kn.no_pair_tail) {
                             b.pair_tail = pt;
                             b.pp_tail = q;
@@ -568,11 +580,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                             b.pp_tail.num_n_tiles = ocp / 128;
                             const int tt = m_pt * (ocp / 128);
                             b.grid_pair_tail = 2 * (tt < pairs ? tt : pairs);
-                            rows_done += m_pt * 2 * umma_conv::kBM;
+                            rows_done += m_pt * 2 * stride;
                         }
                         const int rows_left = p.M_total - rows_done;
                         if (rows_left > 0) {
-                            const int m_left = (rows_left + umma_conv::kBM - 1) / umma_conv::kBM;
+                            const int m_left = (rows_left + stride - 1) / stride;
                             b.umma_tail = et;
                             b.up_tail = p;
                             b.up_tail.m_base = rows_done;
@@ -589,7 +601,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // order, so results do not change (tests: batch invariance, 2 GPUs == 1 GPU).
                 // Measured: worth it for the 256 x 256 tiles (block 7: 1.98 -> 1.89 ms); 128 x 256 tiles cut any
                 // finer become L2-bandwidth bound and the tail costs as much as the wave it replaces.
-                if (!b.pair && !fuse && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
+                if (!b.pair && !fuse && !fuse1 && mt == 2 && p.splits == 1 && !e->key.stage_out && tiles > 2 * sms && tiles % sms != 0 &&
                     !kn.no_tail) {
                     const int main_m = (tiles / sms) * sms / p.num_n_tiles;           // whole m-tiles in the full waves
                     const int rows_left = p.M_total - main_m * mt * umma_conv::kBM;

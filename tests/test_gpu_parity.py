@@ -154,7 +154,7 @@ def test_each_yolo_block_fused_vs_oracle(oracle_libs, layer, batch, precision):
         assert info["kernel"] == "umma_tiled_pool" and info["pool_fused"]
     else:
         assert info["kernel"] == "umma_im2col"
-        assert info["pool_separate"] == (layer == 5)
+        assert not info["pool_separate"] and info["pool_fused"] == (layer == 5)     # block 5: the 2x2/1 pool is fused too
     assert err < (2e-3 if precision == "tf32" else 1.2e-2)
     net.close()
 
@@ -184,6 +184,50 @@ def test_fused_pool_picks_the_reference_maximum(oracle_libs, layer, batch, preci
     oracle_pre = _oracle_block(layer, w, x, pool=False)
     assert normalised_error(prepool, oracle_pre) < (2e-3 if precision == "tf32" else 1.2e-2)
     net.close()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("batch,force_pairs", [(1, False), (3, False), (13, True), (54, True)])
+def test_fused_stride1_pool_picks_the_reference_maximum(oracle_libs, monkeypatch, batch, force_pairs, precision):
+    """Block 5's 2x2 stride-1 SAME pool (max_pool2d_5: pad 0/1 with finfo.min, proj3/dnn_openblas.py:232-235) fused
+    into the im2col epilogue over tiles that overlap by W + 1 rows.  Operator-local identity as above: the oracle's
+    max_pool2d on the dumped pre-pool activations reproduces the fused output bit for bit, same window index
+    (first maximum in (di, dj) raster order, proj3/dnn_openblas.c:7,209-222); and the separate-kernel plan
+    (DNNB_NO_POOL1_FUSION) gives the same bits.  With forced CTA pairs batch 13 runs the pair kernel + the
+    single-CTA tail, batch 54 (9126 rows = 37 + 3 pair tiles of 228 rows + 6 rows) the pair kernel, the 256 x 128
+    pair tail and the single-CTA tail together."""
+    layer = 5
+    w = make_weights(30 + layer, negative_gamma=(batch == 3))[layer]
+    x = np.random.default_rng(50 + layer + batch).standard_normal((batch, 13, 13, CHANNELS[layer])).astype(np.float32)
+    nxt = make_weights(31)[layer + 1]
+    if force_pairs:
+        monkeypatch.setenv("DNNB_PAIR_MIN_TILES", "1")
+    net = _lib.Net(x.shape, [_layer_spec(layer, w), _layer_spec(layer + 1, nxt)], precision=precision)
+    net.forward(x)
+    info = net.block_info(0)
+    assert info["pool_fused"] and not info["pool_separate"]
+    assert info["kernel"] == ("umma_pair" if force_pairs else "umma_im2col")
+    assert info["launches"] == ({13: 2, 54: 3}[batch] if force_pairs else 1)
+    pooled = net.block_output(0)
+    prepool = net.debug_prepool(0, (13, 13))
+    np.testing.assert_array_equal(net.block_output(0), pooled)
+    ref, ref_idx = chain.pool_argmax(prepool, 2, 1)
+    np.testing.assert_array_equal(pooled, ref)
+    padded = np.pad(prepool, [(0, 0), (0, 1), (0, 1), (0, 0)], 'constant', constant_values=np.finfo(np.float32).min)
+    win = np.stack([padded[:, di:di + 13, dj:dj + 13, :] for di in (0, 1) for dj in (0, 1)], axis=-1)
+    got_idx = (win == pooled[..., None]).argmax(-1)
+    np.testing.assert_array_equal(got_idx, ref_idx)
+    oracle_pre = _oracle_block(layer, w, x, pool=False)
+    assert normalised_error(prepool, oracle_pre) < (2e-3 if precision == "tf32" else 1.2e-2)
+    second = net.block_output(1)
+    net.close()
+    monkeypatch.setenv("DNNB_NO_POOL1_FUSION", "1")
+    sep = _lib.Net(x.shape, [_layer_spec(layer, w), _layer_spec(layer + 1, nxt)], precision=precision)
+    sep.forward(x)
+    assert sep.block_info(0)["pool_separate"]
+    np.testing.assert_array_equal(sep.block_output(0), pooled)
+    np.testing.assert_array_equal(sep.block_output(1), second)
+    sep.close()
 
 
 # ------------------------------------------------------------------------------- end to end
