@@ -14,8 +14,13 @@
 // Tile = 8 output rows x 128 columns of one image (patch: 10 input rows x 136 pixels).  TMEM
 // columns [16 o, 16 o + 16) accumulate output row o of the tile.  Patch row r feeds the output
 // rows o = r - di, so it is multiplied ONCE by the stacked weights [W(di=2) | W(di=1) | W(di=0)]
-// (N = 48, clipped to 32 / 16 at the tile's top and bottom) into columns starting at 16 max(0, r-2):
-// 20 MMAs per 1024 output pixels.  The epilogue thread of lane m holds all 8 rows of pixel column
+// (N = 48, clipped to 32 / 16 at the tile's top and bottom) into columns starting at 16 max(0, r-2).
+// An MMA's K slice is two 16-byte units = two (patch row, tap) pairs, and a patch row has three taps: the slice
+// [dj 0 | dj 1] of row r is one MMA (leading byte offset 16: the next pixel), and the left-over taps dj 2 of rows r
+// and r + 1 share another one (leading byte offset = one patch row) against a 64-row operand that covers the four
+// output rows r-2 .. r+1 the two of them feed -- 15 MMAs per 1024 output pixels instead of 20 with a half-empty
+// [dj 2 | -] slice per row.  What bounds this kernel is the shared-memory data path (the MMAs' operand fetch is
+// more than half of it, profiles/r02_SUMMARY.md), so a quarter fewer operand bytes is a quarter less of that.  The epilogue thread of lane m holds all 8 rows of pixel column
 // m: vertical max in registers, horizontal max by one shuffle with lane m ^ 1.
 //
 // The tiles are small, so every per-tile handshake counts: measured on B200 the barrier skeleton
@@ -55,8 +60,9 @@ constexpr int kTileGroups = kGroups * kPatchRows;  // 340
 constexpr int kRounds = (kTileGroups + kProducerWarps * 32 - 1) / (kProducerWarps * 32);   // 2
 constexpr int kPatchRowBytes = kPatchPx * 16;
 constexpr int kPatchBytes = kPatchRows * kPatchRowBytes;
-constexpr int kWOperandBytes = 2 * 48 * 16;        // one stacked operand: 2 K halves x 48 rows x 16 B
-constexpr int kWBytes = 2 * kWOperandBytes;        // tap pairs (dj 0,1) and (dj 2, -)
+constexpr int kWOperandBytes = 2 * 48 * 16;        // operand 0, taps (dj 0, dj 1) of one patch row: 2 K halves x 48 rows x 16 B
+constexpr int kW2OperandBytes = 2 * 64 * 16;       // operand 1, tap dj 2 of TWO consecutive patch rows: 2 K halves x 64 rows
+constexpr int kWBytes = kWOperandBytes + kW2OperandBytes;
 constexpr int kRawDepth = 6;                       // raw-pixel staging ring: tiles whose global loads are in flight
 constexpr int kRawRowBytes = kPatchPx * 12;        // one patch row of raw 12-byte pixels (= kGroups * 48)
 constexpr int kRawBytes = (kPatchRows * kRawRowBytes + 127) / 128 * 128;
@@ -81,14 +87,8 @@ struct Params {
     const float *scale;  // [16]
     const float *shift;  // [16]
     int B, H, W;         // H % 8 == 0, W % 4 == 0
-    int col_tiles;       // column tiles per row tile: ceil(W / 128), or W / 128 when the narrow remainder is packed
-    int num_tiles;       // B * tiles_per_image
-    // Packed narrow tiles (pack >= 2): W = 128 col_tiles + narrow.  Instead of a column tile that carries only
-    // `narrow` valid pixels through 128 MMA rows, the narrow right-hand parts of `pack` consecutive row tiles
-    // share one tile: segment s = MMA rows [seg_pitch s, seg_pitch s + narrow), seg_pitch = narrow + 2 (each
-    // segment has its own one-pixel halo in the patch).  An image is then (H/8) col_tiles ordinary tiles
-    // followed by ceil((H/8) / pack) packed ones.  416 columns: 174 tiles per image instead of 208.
-    int pack, seg_pitch, narrow, tiles_per_image;
+    int col_tiles;       // column tiles per row tile: ceil(W / 128)
+    int num_tiles;       // B * (H / 8) * col_tiles
     int leaky, round_tf32;
     int pool_first;      // every scale[c] > 0: scale/shift, LeakyReLU and rounding are then monotone, so the
                          // epilogue pools the raw accumulators and activates one value instead of four
@@ -145,59 +145,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     const int per_cta = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_begin = (int)blockIdx.x * per_cta;
     const int my_tiles = max(0, min(p.num_tiles, tile_begin + per_cta) - tile_begin);
-    // tile -> (column tile ct, row tile jt, image n), advanced incrementally.  With packing, ct == col_tiles
-    // marks a packed tile whose first row tile is jt.
+    // tile -> (column tile ct, row tile jt, image n), advanced incrementally
     struct Coord { int ct, jt, n; };
     auto decode = [&](int tile) {
         Coord c;
-        c.n = tile / p.tiles_per_image;
-        const int t = tile - c.n * p.tiles_per_image;
-        if (t < row_tiles * p.col_tiles) {
-            c.ct = t % p.col_tiles;
-            c.jt = t / p.col_tiles;
-        } else {
-            c.ct = p.col_tiles;
-            c.jt = (t - row_tiles * p.col_tiles) * p.pack;
-        }
+        c.ct = tile % p.col_tiles;
+        c.jt = (tile / p.col_tiles) % row_tiles;
+        c.n = tile / (p.col_tiles * row_tiles);
         return c;
     };
     auto advance = [&](Coord &c, int steps) {
-        for (int i = 0; i < steps; ++i) {
-            if (c.ct < p.col_tiles) {
-                if (++c.ct == p.col_tiles) {
-                    c.ct = 0;
-                    if (++c.jt == row_tiles) {
-                        c.jt = 0;
-                        if (p.pack) c.ct = p.col_tiles;       // the image's packed tiles follow
-                        else ++c.n;
-                    }
-                }
-            } else {
-                c.jt += p.pack;
-                if (c.jt >= row_tiles) { c.ct = 0; c.jt = 0; ++c.n; }
-            }
+        c.ct += steps;
+        while (c.ct >= p.col_tiles) {
+            c.ct -= p.col_tiles;
+            if (++c.jt == row_tiles) { c.jt = 0; ++c.n; }
         }
     };
-    const int w0_packed = p.col_tiles * 128;
+    const uint32_t patch_base = ptx::smem_u32(s_patch);
+    const uint32_t raw_base = ptx::smem_u32(s_raw);
 
     if (warp < kProducerWarps) {
         // ------------------------------------------------------------ patch producers
         // One pixel per lane: 1360 patch pixels, thread handles pixels tid, tid + 256, ...  Lane L of a warp
         // then writes the 16-byte unit of pixel base + L, i.e. a warp store covers 512 contiguous bytes in the
-        // minimum of 4 shared-memory wavefronts (writing a 4-pixel group per thread, lanes 64 bytes apart,
-        // cost 16: measured, more than half of all the kernel's shared-memory wavefronts were store
-        // conflicts), and its three 4-byte loads at a 12-byte lane stride are conflict-free too.
-        // The pixel -> (patch row, column) split does not depend on the tile: hoist it.
+        // minimum of 4 shared-memory wavefronts, and its three 4-byte loads at a 12-byte lane stride are
+        // conflict-free too.  Everything that does not depend on the tile is hoisted: per pixel and tile the loop
+        // is three shared loads, three adds (or table look-ups), one select per word and one 16-byte store, all
+        // through explicit shared-space accesses (round 1's version went through generic pointers and predicated
+        // blocks: three times the instructions, and these eight warps were the busiest role of the kernel).
         constexpr int kPx = kPatchRows * kPatchPx;                               // 1360
         constexpr int kPxRounds = (kPx + kProducerWarps * 32 - 1) / (kProducerWarps * 32);   // 6
-        int px_row[kPxRounds], px_col[kPxRounds], px_src[kPxRounds];
+        int px_row[kPxRounds], px_col[kPxRounds];
+        uint32_t px_src[kPxRounds];
 #pragma unroll
         for (int it = 0; it < kPxRounds; ++it) {
             const int i = threadIdx.x + kProducerWarps * 32 * it;
             const int r = i / kPatchPx, x = i - r * kPatchPx;
             px_row[it] = i < kPx ? r : 1 << 20;                     // pixels past the patch fail the row test below
             px_col[it] = x - 4;
-            px_src[it] = IN_U8 ? r * kRawRowBytesU8 + (x - 4 + kRawLeadU8) * 3 : i * 12;
+            px_src[it] = i < kPx ? (IN_U8 ? r * kRawRowBytesU8 + (x - 4 + kRawLeadU8) * 3 : i * 12) : 0;
         }
         Coord tc = decode(tile_begin);
         for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
@@ -205,53 +191,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             const int slot = t % kRawDepth, stage = t % kStages;
             ptx::mbar_wait(bar_rfull + 8 * slot, (t / kRawDepth) & 1);        // raw pixels have landed
             ptx::mbar_wait(bar_empty + 8 * stage, ((t / kStages) & 1) ^ 1);    // patch slot is free
-            uint4 *patch = reinterpret_cast<uint4 *>(s_patch + stage * kPatchBytes);
-            const uint8_t *raw = s_raw + slot * kRawBytes;
-            const bool packed = tc.ct == p.col_tiles;
+            const uint32_t patch = patch_base + stage * kPatchBytes + threadIdx.x * 16;
+            const uint32_t raw = raw_base + slot * kRawBytes;
 #pragma unroll
             for (int it = 0; it < kPxRounds; ++it) {
-                if (px_row[it] < kPatchRows) {
-                    bool ok;
-                    int src_off;
-                    if (!packed) {
-                        ok = (unsigned)(row0 + px_row[it]) < (unsigned)p.H && (unsigned)(w0 + px_col[it]) < (unsigned)p.W;
-                        src_off = px_src[it];
+                if (it < kPxRounds - 1 || px_row[it] < kPatchRows) {           // only the last round is partial
+                    const bool ok = (unsigned)(row0 + px_row[it]) < (unsigned)p.H && (unsigned)(w0 + px_col[it]) < (unsigned)p.W;
+                    uint32_t o0, o1, o2;
+                    if constexpr (IN_U8) {
+                        // the table holds the finished operand bits of float32(v / 255.)
+                        const uint8_t *src = s_raw + slot * kRawBytes + px_src[it];
+                        const uint32_t v0 = s_lut[src[0]], v1 = s_lut[src[1]], v2 = s_lut[src[2]];
+                        const uint32_t c0 = p.swap_rb ? v2 : v0, c2 = p.swap_rb ? v0 : v2;
+                        if constexpr (BF16) { o0 = c0 | (v1 << 16); o1 = c2; o2 = 0; }
+                        else { o0 = c0; o1 = v1; o2 = c2; }
                     } else {
-                        // patch pixel x = px_col + 4 belongs to segment (x - 3) / seg_pitch, its column cx there is
-                        // image column w0 - 1 + cx of row tile jt + segment; raw rows are stored [segment][row]
-                        constexpr int lead = IN_U8 ? kRawLeadU8 : 4, px_bytes = IN_U8 ? 3 : 12;
-                        const int xs = px_col[it] + 1;
-                        const int sg = xs >= 0 ? xs / p.seg_pitch : p.pack;
-                        const int cx = xs - sg * p.seg_pitch;
-                        const int irow = kTileRows * (tc.jt + sg) - 1 + px_row[it];
-                        ok = sg < p.pack && tc.jt + sg < row_tiles && (unsigned)irow < (unsigned)p.H &&
-                             (unsigned)(w0_packed - 1 + cx) < (unsigned)p.W;
-                        src_off = ((sg * kPatchRows + px_row[it]) * (p.narrow + 2 * lead) + cx - 1 + lead) * px_bytes;
-                    }
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);                        // outside the image: zeros (SAME padding)
-                    if (ok) {
-                        if constexpr (IN_U8) {
-                            // the table holds the finished operand bits of float32(v / 255.)
-                            const uint8_t *src = raw + src_off;
-                            const uint32_t v0 = s_lut[src[0]], v1 = s_lut[src[1]], v2 = s_lut[src[2]];
-                            const uint32_t c0 = p.swap_rb ? v2 : v0, c2 = p.swap_rb ? v0 : v2;
-                            if constexpr (BF16) { o.x = c0 | (v1 << 16); o.y = c2; }
-                            else { o.x = c0; o.y = v1; o.z = c2; }
+                        uint32_t f0, f1, f2;
+                        const uint32_t a = raw + px_src[it];
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(f0) : "r"(a));
+                        asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(f1) : "r"(a));
+                        asm volatile("ld.shared.b32 %0, [%1+8];" : "=r"(f2) : "r"(a));
+                        if constexpr (BF16) {
+                            __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f0), __uint_as_float(f1));
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(f2), 0.f);
+                            o0 = *reinterpret_cast<uint32_t *>(&rg);
+                            o1 = *reinterpret_cast<uint32_t *>(&b0);
+                            o2 = 0;
                         } else {
-                            const uint32_t *src = reinterpret_cast<const uint32_t *>(raw + src_off);
-                            const uint32_t f0 = src[0], f1 = src[1], f2 = src[2];
-                            if constexpr (BF16) {
-                                __nv_bfloat162 rg = __floats2bfloat162_rn(__uint_as_float(f0), __uint_as_float(f1));
-                                __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(f2), 0.f);
-                                o.x = *reinterpret_cast<uint32_t *>(&rg);
-                                o.y = *reinterpret_cast<uint32_t *>(&b0);
-                            } else {
-                                // round to nearest TF32: add half an ulp; the MMA drops the low 13 bits itself
-                                o.x = f0 + 0x1000u; o.y = f1 + 0x1000u; o.z = f2 + 0x1000u;
-                            }
+                            // round to nearest TF32: add half an ulp; the MMA drops the low 13 bits itself
+                            o0 = f0 + 0x1000u; o1 = f1 + 0x1000u; o2 = f2 + 0x1000u;
                         }
                     }
-                    patch[threadIdx.x + kProducerWarps * 32 * it] = o;
+                    if (!ok) { o0 = 0; o1 = 0; o2 = 0; }                         // outside the image: zeros (SAME padding)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(patch + kProducerWarps * 32 * 16 * it), "r"(o0),
+                                 "r"(o1), "r"(o2), "r"(0u) : "memory");
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -264,37 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     } else if (warp == kLoaderWarp) {
         // ------------------------------------------------------------ raw-pixel loader (one thread)
         if (ptx::elect_one()) {
-            const uint32_t raw_base = ptx::smem_u32(s_raw);
             Coord tc = decode(tile_begin);
             for (int t = 0; t < my_tiles; ++t, advance(tc, 1)) {
                 const int slot = t % kRawDepth;
                 ptx::mbar_wait(bar_rempty + 8 * slot, ((t / kRawDepth) & 1) ^ 1);
                 constexpr int lead = IN_U8 ? kRawLeadU8 : 4, span = IN_U8 ? kRawPxU8 : kPatchPx;
                 constexpr int px_bytes = IN_U8 ? 3 : 12, row_bytes = IN_U8 ? kRawRowBytesU8 : kRawRowBytes;
-                if (tc.ct == p.col_tiles) {
-                    // packed tile: per segment (row tile jt + sg) the rows of columns [w0 - lead, W), stored [segment][row]
-                    const int nseg = min(p.pack, row_tiles - tc.jt);
-                    const uint32_t bytes = (uint32_t)(p.W - (w0_packed - lead)) * px_bytes;     // a multiple of 16
-                    const int seg_row_bytes = (p.narrow + 2 * lead) * px_bytes;
-                    uint32_t rows = 0;
-                    for (int sg = 0; sg < nseg; ++sg) {
-                        const int row0 = kTileRows * (tc.jt + sg) - 1;
-                        rows += (uint32_t)((row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0) - (row0 < 0 ? -row0 : 0));
-                    }
-                    ptx::mbar_expect_tx(bar_rfull + 8 * slot, bytes * rows);
-                    for (int sg = 0; sg < nseg; ++sg) {
-                        const int row0 = kTileRows * (tc.jt + sg) - 1;
-                        const int r_lo = row0 < 0 ? -row0 : 0;
-                        const int r_hi = row0 + kPatchRows <= p.H ? kPatchRows : p.H - row0;
-                        const uint8_t *src = static_cast<const uint8_t *>(p.in) +
-                                             (((size_t)tc.n * p.H + (row0 + r_lo)) * p.W + (w0_packed - lead)) * px_bytes;
-                        uint32_t dst = raw_base + slot * kRawBytes + (sg * kPatchRows + r_lo) * seg_row_bytes;
-                        for (int r = r_lo; r < r_hi; ++r, src += (size_t)p.W * px_bytes, dst += seg_row_bytes)
-                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar_rfull + 8 * slot) : "memory");
-                    }
-                    continue;
-                }
                 const int row0 = kTileRows * tc.jt - 1, w0 = tc.ct * 128;
                 const int px_lo = w0 - lead > 0 ? w0 - lead : 0;
                 const int px_hi = w0 + span - lead < p.W ? w0 + span - lead : p.W;
@@ -315,19 +263,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         if (ptx::elect_one()) {
             constexpr uint32_t fmt = BF16 ? 1u : 2u;
             // descriptor words: lo = start >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version; no swizzle.
-            // A: LBO 16 (next pixel = next tap), SBO 128 (next 8 pixels).  B: LBO 768 (48 rows), SBO 128.
+            // A: SBO 128 (next 8 pixels); LBO 16 (next pixel = next tap) or one patch row (the same tap of the next row).
+            // B: SBO 128; LBO = rows of the operand x 16 (48 rows: 768, 64 rows: 1024).
             constexpr uint32_t HI = (128u >> 4) | (1u << 14);
             const uint32_t w_lo0 = (ptx::smem_u32(s_w) >> 4) | ((768u >> 4) << 16);
+            const uint32_t w2_lo0 = ((ptx::smem_u32(s_w) + kWOperandBytes) >> 4) | ((1024u >> 4) << 16);
             for (int t = warp - kProducerWarps; t < my_tiles; t += kMmaWarps) {
                 const int stage = t % kStages, acc = t % kAccStages;
                 ptx::mbar_wait(bar_tempty + 8 * acc, ((t / kAccStages) & 1) ^ 1);
                 ptx::mbar_wait(bar_full + 8 * stage, (t / kStages) & 1);
                 ptx::tc_fence_after();
-                const uint32_t a_lo0 = (ptx::smem_u32(s_patch + stage * kPatchBytes) >> 4) | ((16u >> 4) << 16);
+                const uint32_t a_base = (patch_base + stage * kPatchBytes) >> 4;
                 const uint32_t d = tmem_base + acc * kAccCols;
-                // Patch row r feeds output rows o in [max(0, r-2), min(7, r)] with di = r - o: the stacked
-                // operand [W2|W1|W0] from row 16 (2 - (r - o_lo)), N = 16 (#rows), into columns 16 o_lo.
-                // Rows 2, 5, 8 go first: together they touch every column once and initialise it.
+                // Taps (dj 0, dj 1) of patch row r feed output rows o in [max(0, r-2), min(7, r)] with di = r - o: the
+                // stacked operand [W2|W1|W0] from row 16 (2 - (r - o_lo)), N = 16 (#rows), into columns 16 o_lo.
+                // Rows 2, 5, 8 go first: together they touch every column exactly once and initialise it.
 #pragma unroll
                 for (int oi = 0; oi < kPatchRows; ++oi) {
                     const int r = oi < 3 ? 2 + 3 * oi : (oi == 3 ? 0 : oi == 4 ? 1 : oi == 5 ? 3 : oi == 6 ? 4 : oi == 7 ? 6 : oi == 8 ? 7 : 9);
@@ -335,15 +285,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                     const int o_hi = r < kTileRows - 1 ? r : kTileRows - 1;
                     const int n = 16 * (o_hi - o_lo + 1);
                     const int wrow = 16 * (2 - (r - o_lo));
-                    const uint32_t idesc = ptx::umma_idesc(fmt, n);
+                    // A rows: pixel m, taps dj = 0, 1  ->  patch pixels m + 3, m + 4
+                    const uint32_t a_lo = a_base + ((r * kPatchRowBytes + 3 * 16) >> 4) + ((16u >> 4) << 16);
+                    ptx::umma<BF16>(d + 16 * o_lo, ptx::umma_desc_join(a_lo, HI), ptx::umma_desc_join(w_lo0 + ((wrow * 16) >> 4), HI),
+                                    ptx::umma_idesc(fmt, n), oi >= 3 ? 1u : 0u);
+                }
+                // Tap dj 2 of patch rows r and r + 1 (r even): K halves (row r, pixel m + 5) and (row r + 1, pixel m + 5),
+                // output rows o in [max(0, r-2), min(7, r+1)].  Operand 1 has 64 rows, 16 (o - (r - 2)) + oc, with
+                // W[r - o][2] in the first half and W[r + 1 - o][2] in the second (zero where di leaves 0..2).
 #pragma unroll
-                    for (int pr = 0; pr < 2; ++pr) {
-                        // A rows: pixel m, taps dj = 2*pr, 2*pr+1  ->  patch pixel m + dj + 3
-                        const uint32_t a_off = (r * kPatchRowBytes + (3 + 2 * pr) * 16) >> 4;
-                        const uint32_t b_off = (pr * kWOperandBytes + wrow * 16) >> 4;
-                        ptx::umma<BF16>(d + 16 * o_lo, ptx::umma_desc_join(a_lo0 + a_off, HI), ptx::umma_desc_join(w_lo0 + b_off, HI),
-                                        idesc, (oi >= 3 || pr != 0) ? 1u : 0u);
-                    }
+                for (int r = 0; r < kPatchRows; r += 2) {
+                    const int o_lo = r - 2 > 0 ? r - 2 : 0;
+                    const int o_hi = r + 1 < kTileRows - 1 ? r + 1 : kTileRows - 1;
+                    const int n = 16 * (o_hi - o_lo + 1);
+                    const int wrow = 16 * (o_lo - (r - 2));
+                    const uint32_t a_lo = a_base + ((r * kPatchRowBytes + 5 * 16) >> 4) + (((uint32_t)kPatchRowBytes >> 4) << 16);
+                    ptx::umma<BF16>(d + 16 * o_lo, ptx::umma_desc_join(a_lo, HI), ptx::umma_desc_join(w2_lo0 + ((wrow * 16) >> 4), HI),
+                                    ptx::umma_idesc(fmt, n), 1u);
                 }
                 ptx::umma_commit(bar_empty + 8 * stage);
                 ptx::umma_commit(bar_tfull + 8 * acc);
@@ -362,20 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         for (int c = 0; c < 8; ++c) { sc8[c] = s_scale[(odd ? 8 : 0) + c]; sh8[c] = s_shift[(odd ? 8 : 0) + c]; }
         Coord tc = decode(tile_begin + group);
         for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
-            const int ct = tc.ct, n = tc.n;
-            int jt = tc.jt, w = ct * 128 + m;
-            bool valid = w < p.W;
-            const bool packed = ct == p.col_tiles;
-            if (packed) {                              // lane m = segment m / seg_pitch, column m % seg_pitch of row tile jt + segment
-                const int sg = m / p.seg_pitch, cx = m - sg * p.seg_pitch;
-                jt += sg;
-                w = w0_packed + cx;
-                valid = sg < p.pack && cx < p.narrow && jt < row_tiles;
-            }
+            const int ct = tc.ct, n = tc.n, jt = tc.jt;
+            const int w = ct * 128 + m;
+            const bool valid = w < p.W;
             const int acc = t % kAccStages;
             ptx::mbar_wait(bar_tfull + 8 * acc, (t / kAccStages) & 1);
             ptx::tc_fence_after();
-            if (packed || ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
+            if (ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
 #pragma unroll 1
                 for (int rp = 0; rp < kTileRows / 2; ++rp) {      // pooling row pairs of the tile
                     uint32_t raw[32];                             // [0,16): output row 2rp, [16,32): row 2rp+1
@@ -459,33 +410,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
     if (warp == kProducerWarps) ptx::tmem_dealloc(tmem_base, kAccCols * kAccStages);
 }
 
-// Host side: the two stacked weight operands (tap pair pr = 0: dj 0,1; pr = 1: dj 2 and a zero tap),
-// each in the canonical no-swizzle K-major layout
-//   elem(nrow, k) -> (k / KC) * 768 + (nrow / 8) * 128 + (nrow % 8) * 16 + (k % KC) * ES
-// with KC = elements per 16 bytes.  Rows 0-15 hold W[di=2], 16-31 W[di=1], 32-47 W[di=0] (row = 16 (2-di) + oc),
-// so any patch row's set of output rows is a contiguous run of operand rows.  K index = (dj - 2 pr) KC + c;
-// channels c >= 3 and tap dj = 3 are zero.  kernel: HWIO [3][3][3][16] fp32.
-// rnd(): value -> operand bit pattern (tf32-rounded fp32 or bf16).
+// Host side: the two stacked weight operands, each in the canonical no-swizzle K-major layout
+//   elem(nrow, k) -> (k / KC) * 16 ROWS + (nrow / 8) * 128 + (nrow % 8) * 16 + (k % KC) * ES
+// with KC = elements per 16 bytes and ROWS the operand's row count.
+//   operand 0 (48 rows): rows 0-15 hold W[di=2], 16-31 W[di=1], 32-47 W[di=0] (row = 16 (2-di) + oc), so any patch
+//     row's set of output rows is a contiguous run of operand rows; K halves = taps dj 0, dj 1.
+//   operand 1 (64 rows), tap dj 2 of patch rows r (first K half) and r + 1 (second half): row = 16 j + oc stands for
+//     output row o = r - 2 + j, j = 0..3; first half W[di = 2 - j][2] (j <= 2), second half W[di = 3 - j][2] (j >= 1).
+// Channels c >= 3 are zero.  kernel: HWIO [3][3][3][16] fp32.  rnd(): value -> operand bit pattern.
 template <typename Elem, typename Rnd>
 void pack_weights(const float *kernel, Elem *out /* kWBytes */, Rnd rnd) {
     static_assert(sizeof(Elem) == 4 || sizeof(Elem) == 2, "fp32 (tf32) or bf16 operands");
     for (int i = 0; i < kWBytes / (int)sizeof(Elem); ++i) out[i] = rnd(0.f);
-    for (int pr = 0; pr < 2; ++pr) {
-        Elem *op = out + (size_t)pr * kWOperandBytes / sizeof(Elem);
-        for (int di = 0; di < 3; ++di)
-            for (int oc = 0; oc < 16; ++oc) {
-                const int nrow = 16 * (2 - di) + oc;
-                for (int half = 0; half < 2; ++half) {
-                    const int dj = 2 * pr + half;
-                    if (dj > 2) continue;
-                    for (int c = 0; c < 3; ++c) {
-                        const float wv = kernel[((size_t)(di * 3 + dj) * 3 + c) * 16 + oc];
-                        const size_t byte = (size_t)half * 768 + (nrow / 8) * 128 + (nrow % 8) * 16 + c * sizeof(Elem);
-                        op[byte / sizeof(Elem)] = rnd(wv);
-                    }
-                }
-            }
-    }
+    auto put = [&](Elem *op, int rows, int nrow, int half, int di, int dj) {
+        for (int c = 0; c < 3; ++c) {
+            const float wv = kernel[((size_t)(di * 3 + dj) * 3 + c) * 16 + (nrow % 16)];
+            const size_t byte = (size_t)half * rows * 16 + (nrow / 8) * 128 + (nrow % 8) * 16 + c * sizeof(Elem);
+            op[byte / sizeof(Elem)] = rnd(wv);
+        }
+    };
+    for (int di = 0; di < 3; ++di)
+        for (int oc = 0; oc < 16; ++oc)
+            for (int half = 0; half < 2; ++half) put(out, 48, 16 * (2 - di) + oc, half, di, half);
+    Elem *op1 = out + kWOperandBytes / sizeof(Elem);
+    for (int j = 0; j < 4; ++j)
+        for (int oc = 0; oc < 16; ++oc) {
+            if (j <= 2) put(op1, 64, 16 * j + oc, 0, 2 - j, 2);
+            if (j >= 1) put(op1, 64, 16 * j + oc, 1, 3 - j, 2);
+        }
 }
 
 }  // namespace conv0

@@ -25,7 +25,6 @@ struct Knobs {
     bool no_graph = false;           // DNNB_NO_GRAPH         latency plan without CUDA-graph replay
     bool force_simt = false;         // DNNB_FORCE_SIMT       CUDA-core kernels everywhere
     bool no_conv0 = false;           // DNNB_NO_CONV0         block 0 through the generic kernel (after a cast)
-    bool conv0_pack = false;         // DNNB_CONV0_PACK=1     block 0: narrow remainders of the width packed three row tiles to a tile
     bool no_rowpair = false;         // DNNB_NO_ROWPAIR       blocks 1-2 through the generic kernel
     int rowpair_linear = -1;         // DNNB_ROWPAIR_LINEAR=0|1 force / DNNB_NO_ROWPAIR_LINEAR: linearised tiles off
     int rowpair_max_tr = 8;          // DNNB_ROWPAIR_MAX_TR   cap on the row-pair tile height
@@ -58,7 +57,7 @@ struct KnobDef {
 };
 const KnobDef g_knob_defs[] = {
     {"DNNB_LATENCY_MODE", true, 0, 1},     {"DNNB_NO_PDL", true, 0, 1},          {"DNNB_NO_GRAPH", true, 0, 1},
-    {"DNNB_FORCE_SIMT", true, 0, 1},       {"DNNB_NO_CONV0", true, 0, 1},        {"DNNB_CONV0_PACK", true, 0, 1},
+    {"DNNB_FORCE_SIMT", true, 0, 1},       {"DNNB_NO_CONV0", true, 0, 1},        
     {"DNNB_NO_ROWPAIR", true, 0, 1},       {"DNNB_ROWPAIR_LINEAR", true, 0, 1},  {"DNNB_NO_ROWPAIR_LINEAR", true, 0, 1},
     {"DNNB_ROWPAIR_MAX_TR", false, 2, 8},  {"DNNB_NO_POOL_FIRST", true, 0, 1},   {"DNNB_NO_STAGE_OUT", true, 0, 1},
     {"DNNB_NO_MT2", true, 0, 1},           {"DNNB_MT2_MASK", false, 0, 1 << 20}, {"DNNB_NO_PAIR", true, 0, 1},
@@ -115,7 +114,6 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.no_graph = value("DNNB_NO_GRAPH", 0) != 0;
     k.force_simt = value("DNNB_FORCE_SIMT", 0) != 0;
     k.no_conv0 = value("DNNB_NO_CONV0", 0) != 0;
-    k.conv0_pack = value("DNNB_CONV0_PACK", 0) != 0;
     k.no_rowpair = value("DNNB_NO_ROWPAIR", 0) != 0;
     const int lin_on = getenv("DNNB_ROWPAIR_LINEAR") ? value("DNNB_ROWPAIR_LINEAR", -1) : -1;
     k.rowpair_linear = lin_on >= 0 ? lin_on : (value("DNNB_NO_ROWPAIR_LINEAR", 0) != 0 ? 0 : -1);
@@ -376,21 +374,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         c = conv0::Params{};
         c.B = net->B; c.H = b.ih; c.W = b.iw;
         c.col_tiles = (b.iw + 127) / 128;
-        const int row_tiles = b.ih / conv0::kTileRows;
-        c.tiles_per_image = row_tiles * c.col_tiles;
-        // a narrow remainder of the width (416 = 3 x 128 + 32): pack the narrow parts of several row tiles into one
-        // tile instead of spending a whole column tile on each (conv0_umma.cuh, Params::pack)
-        const int narrow = b.iw % 128, pitch = narrow + 2;
-        if (kn.conv0_pack && b.iw >= 128 && narrow > 0 && narrow % 16 == 0 && b.iw % 16 == 0 && 128 / pitch >= 2 &&
-            (128 / pitch) * conv0::kPatchRows * (narrow + 8) * 12 <= conv0::kRawBytes &&
-            (128 / pitch) * conv0::kPatchRows * (narrow + 2 * conv0::kRawLeadU8) * 3 <= conv0::kRawBytes) {
-            c.pack = 128 / pitch;
-            c.seg_pitch = pitch;
-            c.narrow = narrow;
-            c.col_tiles = b.iw / 128;
-            c.tiles_per_image = row_tiles * c.col_tiles + (row_tiles + c.pack - 1) / c.pack;
-        }
-        c.num_tiles = net->B * c.tiles_per_image;
+        c.num_tiles = net->B * (b.ih / conv0::kTileRows) * c.col_tiles;
         c.leaky = b.leaky; c.round_tf32 = b.round_tf32;
         c.pool_first = all_scales_positive(b) && !kn.no_pool_first;
         b.grid = c.num_tiles < net->num_sms ? c.num_tiles : net->num_sms;

@@ -587,30 +587,6 @@ def test_uint8_frames_match_numpy_preprocessing():
     eng.close()
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-def test_conv0_packed_narrow_tiles_equal_the_default_tiling(monkeypatch, precision):
-    """DNNB_CONV0_PACK=1: the 32-column remainder of the 416-pixel rows of three row tiles shares one tile
-    (174 instead of 208 tiles per image).  Same MMAs per output pixel, so the block's output must be
-    bit-identical to the default tiling, from float32 images and from uint8 frames, at a batch whose
-    last packed tile is ragged (52 row tiles = 17 x 3 + 1)."""
-    w = make_weights(20, negative_gamma=True)[0]
-    rng = np.random.default_rng(41)
-    frames = rng.integers(0, 256, size=(2, 416, 416, 3), dtype=np.uint8)
-    x = np.asarray((frames / 255.)[:, :, :, ::-1], dtype=np.float32)
-    outs = {}
-    for pack in ("0", "1"):
-        monkeypatch.setenv("DNNB_CONV0_PACK", pack)
-        net = _lib.Net(x.shape, [_layer_spec(0, w)], precision=precision)
-        info = net.block_info(0)
-        assert info["kernel"] == "umma_conv0" and info["tiles"] == 2 * (174 if pack == "1" else 208)
-        outs[pack] = (net.forward(x).copy(), net.forward_u8(frames, bgr=True).copy())
-        net.close()
-    np.testing.assert_array_equal(outs["1"][0], outs["0"][0])
-    np.testing.assert_array_equal(outs["1"][1], outs["0"][1])
-    np.testing.assert_array_equal(outs["1"][1], outs["1"][0])
-    assert normalised_error(outs["1"][0], _oracle_block(0, w, x)) < (2e-3 if precision == "tf32" else 1.2e-2)
-
-
 def test_debug_mode_runs_node_by_node_and_dumps_layers(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     gold = np.load(os.path.join(GOLDEN, "mini_net.npz"))
