@@ -38,6 +38,7 @@
 // get two mbarrier phases ahead would read a stale parity as "complete".
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_bf16.h>
 
 #include "ptx.cuh"
@@ -318,6 +319,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         float sc8[8], sh8[8];                          // scale/shift of the 8 channels this lane stores
 #pragma unroll
         for (int c = 0; c < 8; ++c) { sc8[c] = s_scale[(odd ? 8 : 0) + c]; sh8[c] = s_shift[(odd ? 8 : 0) + c]; }
+        // The three epilogue variants are three separate tile loops, chosen once: inside one loop the compiler
+        // if-converts the variants and every thread issues all of them (round 1's version: 1069 issue slots per
+        // pooling row pair for ~100 useful ones -- after the converters the busiest role of the kernel).
+        //   0: every scale > 0 -> pool the raw accumulators, then activate (the normal case)
+        //   1: activate, then pool (negative scales)          2: as 1, and dump the pooled-over activations (debug)
+        auto epilogue_tiles = [&](auto MODE) {
+            constexpr int mode = decltype(MODE)::value;
         Coord tc = decode(tile_begin + group);
         for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
             const int ct = tc.ct, n = tc.n, jt = tc.jt;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                     ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kAccCols + 32 * rp, raw);
                     ptx::tmem_ld_wait();
                     const int orow = kTileRows * jt + 2 * rp;     // conv output row of raw[0..15]
-                    if (p.prepool != nullptr) {                   // debug dump of the pooled-over activations (cold path)
+                    if constexpr (mode == 2) {                   // debug dump of the pooled-over activations (cold path)
                         for (int c = 0; c < 16; ++c) {
                             float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
                             float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                         }
                     }
                     float r8[8];
-                    if (p.pool_first) {
+                    if constexpr (mode == 0) {
                         // all scales positive: pool the raw accumulators (2 rows here, 2 columns by shuffle),
                         // then scale/shift + LeakyReLU + rounding on the 8 channels this lane stores
 #pragma unroll
@@ -403,6 +411,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
         }
+        };
+        if (p.prepool != nullptr) epilogue_tiles(std::integral_constant<int, 2>{});
+        else if (p.pool_first) epilogue_tiles(std::integral_constant<int, 0>{});
+        else epilogue_tiles(std::integral_constant<int, 1>{});
     }
 
     ptx::tc_fence_before();

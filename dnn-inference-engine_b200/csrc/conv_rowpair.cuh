@@ -21,6 +21,7 @@
 // 2 x 4 epilogue warps that alternate tiles.  One channel chunk only: IC * elem_size must equal the swizzle span (32/64/128 B).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -233,6 +234,12 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m = quarter * 32 + lane;
         const int OW = p.W >> 1;
         const bool odd = lane & 1;
+        // Three epilogue variants as three separate tile loops, chosen once (inside one loop the compiler if-converts
+        // the variants and every thread issues all of them: ~920 issue slots per 16-channel step for ~100 useful ones):
+        //   0: every scale > 0 -> pool the raw accumulators, then activate (the normal case)
+        //   1: activate, then pool (negative scales)          2: as 1, and dump the pooled-over activations (debug)
+        auto epilogue_tiles = [&](auto MODE) {
+            constexpr int mode = decltype(MODE)::value;
         Coord tc = decode(tile_begin + group);
         for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
             int ct = tc.ct, j = tc.j, n = tc.n;
@@ -263,7 +270,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // second row
                     ptx::tmem_ld_wait();
                     float v[16];
-                    if (p.prepool != nullptr && (unsigned)w < (unsigned)p.W) {     // debug dump of the pooled-over activations (cold path)
+                    if (mode == 2 && (unsigned)w < (unsigned)p.W) {     // debug dump of the pooled-over activations (cold path)
                         for (int c = 0; c < 16; ++c) {
                             const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
                             float a = fmaf(__uint_as_float(top[c]), sc, sh);
@@ -276,7 +283,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                     float r8[8];
-                    if (p.pool_first) {
+                    if constexpr (mode == 0) {
                         // all scales positive: max over the 2x2 window of raw accumulators first
                         const float4 sca = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0));
                         const float4 scb = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0) + 4);
@@ -337,6 +344,10 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
         }
+        };
+        if (p.prepool != nullptr) epilogue_tiles(std::integral_constant<int, 2>{});
+        else if (p.pool_first) epilogue_tiles(std::integral_constant<int, 0>{});
+        else epilogue_tiles(std::integral_constant<int, 1>{});
     }
 
     ptx::tc_fence_before();

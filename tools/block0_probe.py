@@ -1,5 +1,6 @@
-"""Runs block 0 alone (micro-batch from argv) through both conv0 kernels so that ncu can capture them:
-  ncu --set full --clock-control none --import-source on -k regex:conv0 -c 4 -o gpurun_out/conv0 python tools/block0_probe.py 512"""
+"""Runs block 0 alone (micro-batch from argv; further arguments NAME=value set planner switches for a second run) so
+that ncu can capture the conv0 kernel:
+  ncu --set full --clock-control none --import-source on -k regex:conv0 -c 2 -o gpurun_out/conv0 python tools/block0_probe.py 512"""
 import os
 import sys
 
@@ -15,7 +16,7 @@ from synth import make_weights  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 spec = bench.yolo_spec(make_weights(0))[:2]
 x = torch.rand((batch, 416, 416, 3), device="cuda")
-for env in ({}, {"DNNB_CONV0_V1": "1"}):
+for env in [{}] + [dict([a.split("=")]) for a in sys.argv[2:]]:
     os.environ.update(env)
     net = _lib.Net((batch, 416, 416, 3), spec, precision="tf32")
     net.debug_block_limit(1)
