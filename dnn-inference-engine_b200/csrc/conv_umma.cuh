@@ -55,6 +55,7 @@ struct Params {
     int leaky;
     int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
     float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
+    int tma_store;        // STAGE_OUT: write the staged rows with bulk async copies (0: per-lane stores; DNNB_NO_TMA_STORE)
     // split-K (small batches: too few output tiles to fill the SMs, weights dominate the traffic):
     // `splits` CTAs share one output tile.  Each stores the partial sums of its K slice to its own
     // slab of `workspace`, bumps `counters[tile]` and waits until all `splits` slabs are there; then
@@ -564,27 +565,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
                 if constexpr (STAGE_OUT) {
-                    // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run
-                    __syncwarp();
+                    // rows are OC floats wide and adjacent in memory: this warp's 32 rows are one contiguous run, written by
+                    // ONE bulk async copy shared -> global (cp.async.bulk: the copy engine streams whole lines, no per-lane
+                    // store instructions) whenever both ends fall on 16-byte boundaries; by hand otherwise
                     const int row0 = p.m_base + m_tile * p.m_stride + quarter * 32;
                     const int rows = min(32, p.M_total - row0);
-                    if (rows > 0) {
-                        const int count = rows * p.OC;
-                        const float *src = s_out + (size_t)quarter * 32 * p.OC;
-                        float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
-                        if ((((size_t)quarter * 32 * p.OC) & 3) == 0 && (((size_t)row0 * p.OC) & 3) == 0) {
-                            for (int i = lane * 4; i + 3 < count; i += 128)
-                                *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
-                            for (int i = (count & ~3) + lane; i < count; i += 32) dst[i] = src[i];
-                        } else {
-                            for (int i = lane; i < count; i += 32) dst[i] = src[i];
+                    const float *src = s_out + (size_t)quarter * 32 * p.OC;
+                    float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
+                    const uint32_t bytes = rows > 0 ? (uint32_t)rows * p.OC * 4 : 0;
+                    const bool bulk = p.tma_store && bytes > 0 && (bytes & 15) == 0 && (ptx::smem_u32(src) & 15) == 0 &&
+                                      (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+                    if (bulk) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the staged rows were written by the generic proxy
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ptx::smem_u32(src)), "r"(bytes) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the staging rows may be rewritten
                         }
+                        __syncwarp();
+                    } else {
+                        __syncwarp();
+                        if (rows > 0) {
+                            const int count = rows * p.OC;
+                            if ((((size_t)quarter * 32 * p.OC) & 3) == 0 && (((size_t)row0 * p.OC) & 3) == 0) {
+                                for (int i = lane * 4; i + 3 < count; i += 128)
+                                    *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
+                                for (int i = (count & ~3) + lane; i < count; i += 32) dst[i] = src[i];
+                            } else {
+                                for (int i = lane; i < count; i += 32) dst[i] = src[i];
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }   // mi
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if constexpr (STAGE_OUT) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // bulk stores have reached global memory
         }
     }
 

@@ -499,6 +499,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 p.m_stride = stride;
                 p.leaky = b.leaky;
                 p.round_tf32 = b.round_tf32;
+                p.tma_store = kn.no_tma_store ? 0 : 1;
                 // split-K when the output tiles alone cannot occupy the SMs (small batches)
                 const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
                 const int kstages = total_kb / kbs;

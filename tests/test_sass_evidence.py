@@ -63,3 +63,13 @@ def test_operands_arrive_by_tma(sass_by_kernel, key):
 def test_conv0_streams_raw_pixels_with_bulk_copies(sass_by_kernel):
     for name, sass in _family(sass_by_kernel, "conv0_kernel").items():
         assert "UBLKCP" in sass, name                        # cp.async.bulk (12-byte pixels: no tensor map possible)
+
+
+def test_staged_output_rows_leave_by_bulk_store(sass_by_kernel):
+    """Block 8 (125 channels = 500-byte rows): the tile is staged in shared memory and written shared -> global by
+    cp.async.bulk (UBLKCP.G.S), not by per-lane stores.  The staged-output instantiations are the ones whose mangled
+    name ends in the STAGE_OUT = true, POOL1 = false template arguments."""
+    staged = {k: v for k, v in _family(sass_by_kernel, "conv_umma_kernel").items() if "UBLKCP.G.S" in v}
+    assert len(staged) == 2, sorted(staged)                  # TF32 and BF16-operand heads
+    for name in staged:
+        assert "Lb1ELb0EEEv" in name, name                   # <..., STAGE_OUT = true, POOL1 = false>
