@@ -64,6 +64,7 @@ _sig("dnnb_net_debug_prepool", c_void_p, c_int, FP)
 _sig("dnnb_net_time_blocks", c_void_p, c_int, c_int, FP)
 _sig("dnnb_net_launches_per_forward", c_void_p, IP)
 _sig("dnnb_net_debug_block_limit", c_void_p, c_int)
+_sig("dnnb_net_debug_timeline", c_void_p, c_int, c_void_p, IP)
 _sig("dnnb_net_profile_block", c_void_p, c_int)
 _sig("dnnb_net_profile_read", c_void_p, FP, IP)
 _sig("dnnb_net_destroy", c_void_p)
@@ -88,7 +89,7 @@ EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
            "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync",
            "dnnb_net_next_slot", "dnnb_net_wait_slot", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
-           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit",
+           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit", "dnnb_net_debug_timeline",
            "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
            "dnnb_postprocess", "dnnb_postprocess_candidates", "dnnb_nms", "dnnb_net_set_detect",
@@ -307,12 +308,13 @@ class Net:
         check(lib.dnnb_net_wait_slot(self._h, slot))
 
     def block_info(self, i):
-        info = (c_int * 13)()
+        info = (c_int * 16)()
         check(lib.dnnb_net_block_info(self._h, i, info))
         v = list(info)
         return {"kernel": KERNEL_NAMES[v[0]], "out_shape": (self.in_shape[0], v[1], v[2], v[3]),
                 "pool_fused": bool(v[4]), "bn_tile": v[5], "swizzle": v[6], "stages": v[7], "grid": v[8],
-                "pool_separate": bool(v[9]), "act_bytes": v[10], "launches": v[11], "tiles": v[12]}
+                "pool_separate": bool(v[9]), "act_bytes": v[10], "launches": v[11], "tiles": v[12],
+                "splits": v[13], "cluster_splitk": bool(v[14])}
 
     def block_output(self, i):
         shape = self.block_info(i)["out_shape"]
@@ -339,6 +341,18 @@ class Net:
         ms, n = c_float(0), c_int(0)
         check(lib.dnnb_net_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def debug_timeline(self, block, read=False):
+        """Arms (read=False) or reads (read=True -> uint64 [ctas, 8] of %globaltimer ns) the per-CTA phase stamps of a block."""
+        n = c_int(0)
+        if not read:
+            check(lib.dnnb_net_debug_timeline(self._h, block, None, ctypes.byref(n)))
+            return n.value
+        check(lib.dnnb_net_debug_timeline(self._h, block, None, ctypes.byref(n))) if False else None
+        grid = self.block_info(block)["grid"]
+        out = np.zeros((grid, 8), dtype=np.uint64)
+        check(lib.dnnb_net_debug_timeline(self._h, block, out.ctypes.data, ctypes.byref(n)))
+        return out[:n.value]
 
     def debug_block_limit(self, blocks):
         check(lib.dnnb_net_debug_block_limit(self._h, blocks))

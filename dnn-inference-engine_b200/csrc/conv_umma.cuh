@@ -67,7 +67,26 @@ struct Params {
     int splits;           // 1 = off
     float *workspace;     // [splits][num_m_tiles * MT * 128][num_n_tiles * BN] fp32
     int *counters;        // [num_m_tiles * num_n_tiles][2]: arrived, departed; zero between launches
+    // Cluster split-K (cluster_splitk = 1, splits in {2, 4, 8, 16}): the `splits` CTAs of an output tile are ONE thread-block
+    // cluster (launch attribute; CTA rank = K slice, so co-scheduling is the hardware's guarantee, not an assumption
+    // about the grid).  Each CTA parks its partial tile in its own shared memory (the ring is idle by then), the
+    // cluster synchronises, and every CTA sums a BN / splits wide column strip of the tile over its peers IN RANK ORDER
+    // through distributed shared memory, then finishes and stores that strip.  No workspace in global memory, no
+    // counters, no spinning -- and rows stay together in one CTA, which is what a fused pool needs.
+    int cluster_splitk;
+    // debug: per-CTA phase stamps (%globaltimer, ns) [gridDim.x][8]: 0 entry, 1 prologue done, 2 predecessor complete
+    // (griddepcontrol.wait returned), 3 first operands landed, 4 last MMA issued, 5 accumulator complete, 6 partial tile
+    // parked / workspace written and all siblings seen, 7 result stored.  NULL in production.
+    unsigned long long *timeline;
 };
+
+__device__ __forceinline__ void stamp(const Params &p, int slot) {
+    if (p.timeline != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 // MT = M tiles (of 128 rows) per CTA tile that share every B tile: MT = 2 turns the CTA tile
 // into 256 x BN, a third less L2->SMEM traffic per flop, at the price of a single accumulator
@@ -109,6 +128,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int BKC = SWZ / ES;            // channels per K-block
     constexpr int MMA_PER_KB = SWZ / 32;     // each MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
     static_assert(!(POOL && IM2COL), "the fused pool needs spatial tiles");
+    constexpr bool kClusterCapable = IM2COL && !POOL && !POOL1 && !STAGE_OUT && MT == 1;     // variants that carry the cluster split-K path
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,14 +152,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int num_tiles = tiles_mn * p.splits;       // work items: (output tile, K slice)
     const int taps = p.KH * p.KW;
     const int num_kstages = taps * p.c_chunks / KBS;
+    // work item -> (output tile, K slice).  Global-workspace split-K orders the items slice-major; cluster split-K
+    // makes the slices of a tile consecutive CTAs (= the ranks of one cluster).
+    auto item_split = [&](int tile) { return p.cluster_splitk ? tile % p.splits : tile / tiles_mn; };
+    auto item_mn = [&](int tile) { return p.cluster_splitk ? tile / p.splits : tile % tiles_mn; };
     // K slice of work item `tile`: stages [ks_lo, ks_hi)
     auto k_range = [&](int tile, int &ks_lo, int &ks_hi) {
-        const int split = tile / tiles_mn;
+        const int split = item_split(tile);
         ks_lo = (int)((long)num_kstages * split / p.splits);
         ks_hi = (int)((long)num_kstages * (split + 1) / p.splits);
     };
 
     ptx::griddep_launch();
+    if (threadIdx.x == 0) stamp(p, 0);
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -157,7 +182,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
     {   // epilogue constants: a CTA with a single work item only needs the columns of its own N tile
         const bool one_tile = num_tiles <= (int)gridDim.x;
-        const int c_lo = one_tile ? ((int)blockIdx.x % p.num_n_tiles) * BN : 0;
+        const int c_lo = one_tile ? (item_mn((int)blockIdx.x) % p.num_n_tiles) * BN : 0;
         const int c_hi = one_tile ? c_lo + BN : p.num_n_tiles * BN;
         for (int i = c_lo + threadIdx.x; i < c_hi; i += kThreads) {
             s_scale[i] = p.scale[i];
@@ -168,9 +193,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 32) stamp(p, 1);
     // Programmatic dependent launch: up to here nothing depends on the preceding kernel.  The producer
     // lane additionally starts the weight tiles of its first stages before it waits.
     if (warp != 0) ptx::griddep_wait();
+    if (threadIdx.x == 32) stamp(p, 2);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -184,7 +211,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 int ks_lo, ks_hi;
                 k_range(blockIdx.x, ks_lo, ks_hi);
                 early = ks_hi - ks_lo < STAGES ? ks_hi - ks_lo : STAGES;
-                const int n_tile = (int)blockIdx.x % p.num_n_tiles;
+                const int n_tile = item_mn((int)blockIdx.x) % p.num_n_tiles;
                 for (int e = 0; e < early; ++e) {
                     const uint32_t full = bar_full + 8 * e;
                     ptx::mbar_expect_tx(full, C::STAGE_BYTES);
@@ -199,8 +226,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             ptx::griddep_wait();
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.num_n_tiles;
-                const int m_tile = (tile % tiles_mn) / p.num_n_tiles;
+                const int n_tile = item_mn(tile) % p.num_n_tiles;
+                const int m_tile = item_mn(tile) / p.num_n_tiles;
                 int ks_lo, ks_hi;
                 k_range(tile, ks_lo, ks_hi);
                 int w0[MT], h0[MT], n0[MT];
@@ -250,6 +277,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
+        if constexpr (kClusterCapable) {       // the cluster barriers of the split-K reduction count every thread of every CTA
+            if (p.cluster_splitk && p.splits > 1 && (int)blockIdx.x < num_tiles) { __syncwarp(); ptx::cluster_sync_all(); ptx::cluster_sync_all(); }
+        }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
@@ -269,6 +299,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int ks = ks_lo; ks < ks_hi; ++ks) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase);
                     ptx::tc_fence_after();
+                    if (ks == ks_lo && local == 0) stamp(p, 3);
                     const uint32_t a_lo = ptx::umma_desc_lo(smem_base + stage * C::STAGE_BYTES);
                     const uint32_t b_lo = a_lo + ((KBS * MT * C::A_TILE) >> 4);
 #pragma unroll
@@ -287,7 +318,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(bar_tfull + 8 * acc);          // accumulator complete
+                stamp(p, 4);
             }
+        }
+        if constexpr (kClusterCapable) {
+            if (p.cluster_splitk && p.splits > 1 && (int)blockIdx.x < num_tiles) { __syncwarp(); ptx::cluster_sync_all(); ptx::cluster_sync_all(); }
         }
     } else {
         // ------------------------------------------------------------------ epilogue
@@ -298,17 +333,117 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             const int acc = local % ACC;
             const uint32_t acc_phase = (local / ACC) & 1;
-            const int n_tile = tile % p.num_n_tiles;
-            const int m_tile = (tile % tiles_mn) / p.num_n_tiles;
+            const int n_tile = item_mn(tile) % p.num_n_tiles;
+            const int m_tile = item_mn(tile) / p.num_n_tiles;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase);
             ptx::tc_fence_after();
+            if (row == 0) stamp(p, 5);
 
             const bool split_k = p.splits > 1;
             const int ldw = p.num_n_tiles * BN;
+            if constexpr (kClusterCapable) {
+                if (split_k && p.cluster_splitk) {
+                    // ---- cluster split-K: park the partial tile in shared memory, reduce a column strip over the peers
+                    constexpr uint32_t PITCH = (BN + 4) * 4;          // bytes per parked row: 16-byte stores stay conflict-free
+                    static_assert(kBM * PITCH <= (uint32_t)STAGES * C::STAGE_BYTES, "the partial tile fits the idle ring");
+                    const uint32_t my_row = smem_base + (uint32_t)row * PITCH;
+#pragma unroll 1
+                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                        uint32_t raw[32];
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + chunk * 32, raw);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (chunk * 32 + j) * 4), "r"(raw[j]),
+                                         "r"(raw[j + 1]), "r"(raw[j + 2]), "r"(raw[j + 3]) : "memory");
+                    }
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(bar_tempty + 8 * acc);
+                    ptx::cluster_sync_all();                          // #1: every peer's partial tile is parked (all warps of all CTAs arrive)
+                    if (row == 0) stamp(p, 6);
+                    const int rank = (int)ptx::cluster_ctarank();     // == item_split(tile)
+                    const int cw = BN / p.splits;                     // strip width in floats: a multiple of 4 (splits <= 16 <= BN / 8)
+                    const int c4n = cw >> 2;                          // 16-byte units per row of the strip
+                    // item = (row, 16-byte unit) of the strip, consecutive threads = consecutive units of a row: a warp's remote
+                    // load is then a few whole 128-byte runs of one peer's shared memory (one scattered 16 bytes per lane ran
+                    // at a tenth of the speed)
+                    for (int item = row; item < kBM * c4n; item += 128) {
+                        const int r = item / c4n, c4 = (item - r * c4n) * 4;
+                        const int m = p.m_base + m_tile * p.m_stride + r;
+                        if (m >= p.M_total) break;                    // rows ascend with the item index
+                        const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + c4) * 4;
+                        float4 t4[16];
+#pragma unroll
+                        for (int peer = 0; peer < 16; ++peer) {       // all peers' loads in flight together, then summed in rank order
+                            if (peer < p.splits)
+                                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(t4[peer].x), "=f"(t4[peer].y), "=f"(t4[peer].z), "=f"(t4[peer].w)
+                                             : "r"(ptx::mapa(src, (uint32_t)peer)));
+                        }
+                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int peer = 0; peer < 16; ++peer) {
+                            if (peer < p.splits) { sum.x += t4[peer].x; sum.y += t4[peer].y; sum.z += t4[peer].z; sum.w += t4[peer].w; }
+                        }
+                        float v4[4] = {sum.x, sum.y, sum.z, sum.w};
+                        const int col = n_tile * BN + rank * cw + c4;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
+                            if (p.leaky) y = fmaxf(y, 0.1f * y);
+                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                            else if (p.round_tf32) y = ptx::round_tf32(y);
+                            v4[e] = y;
+                        }
+                        if constexpr (OUT_BF16) {
+                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
+                        } else {
+                            float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                            if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.OC) o[e] = v4[e];
+                            }
+                        }
+                    }
+                    if (row == 0) stamp(p, 7);
+                    ptx::cluster_sync_all();                          // #2: nobody reads this CTA's shared memory any more
+                    continue;
+                }
+            }
             if (split_k) {
-                const int split = tile / tiles_mn;
+                const int split = item_split(tile);
                 const size_t slab = (size_t)p.num_m_tiles * MT * kBM * ldw;       // floats per K-slice slab
-                // phase 1: this K slice's partial sums -> own slab; free the accumulator
+                // phase 1: this K slice's partial sums -> own slab; free the accumulator.  The tile is parked in the (idle)
+                // shared-memory ring first and leaves as one bulk async copy per row: whole lines written by the copy
+                // engine, instead of 64 scattered 16-byte stores per thread whose completion the fence below then had
+                // to wait for (8 us of a 22 us kernel, tools/batch1_timeline.py).
+                if constexpr (MT == 1) {
+                    constexpr uint32_t PITCH = (BN + 4) * 4;
+                    static_assert(kBM * PITCH <= (uint32_t)STAGES * C::STAGE_BYTES, "the partial tile fits the idle ring");
+                    const uint32_t my_row = smem_base + (uint32_t)row * PITCH;
+#pragma unroll 1
+                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                        uint32_t raw[32];
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + chunk * 32, raw);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (chunk * 32 + j) * 4), "r"(raw[j]),
+                                         "r"(raw[j + 1]), "r"(raw[j + 2]), "r"(raw[j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // parked by the generic proxy, read by the copy engine
+                    if (p.m_base + m_tile * kBM + row < p.M_total) {       // rows past the last pixel are never read back
+                        float *wrow = p.workspace + split * slab + ((size_t)m_tile * kBM + row) * ldw + n_tile * BN;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(wrow), "r"(my_row), "r"(BN * 4) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                } else {
 #pragma unroll 1
                 for (int mi = 0; mi < MT; ++mi) {
                     float4 *wrow = reinterpret_cast<float4 *>(p.workspace + split * slab +
@@ -324,13 +459,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                                       __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
                     }
                 }
+                }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(bar_tempty + 8 * acc);
                 asm volatile("fence.proxy.async;" ::: "memory");      // the siblings read the slabs with bulk copies (async proxy)
                 __threadfence();
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (row == 0) {
-                    int *ctr = p.counters + 2 * (tile % tiles_mn);
+                    int *ctr = p.counters + 2 * item_mn(tile);
                     atomicAdd(ctr, 1);
                     long long t0 = clock64();
                     while (true) {                  // every sibling CTA is resident (grid <= SMs): this terminates
@@ -344,6 +480,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 __threadfence();
                 asm volatile("fence.proxy.async;" ::: "memory");
+                if (row == 0) stamp(p, 6);
                 // phase 2: rows [r0, r1) of the tile are this CTA's share.  Their partial sums in every slab are
                 // pulled into the (now idle) smem ring by bulk copies, one per (slab, row), all in flight at once
                 // -- one L2 round trip instead of one per group of loads -- then summed IN SLAB ORDER, finished
@@ -358,7 +495,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 // when there are any).  The last sibling to leave resets the pair for the next launch.
                 auto depart = [&]() {
                     if (row == 0) {
-                        int *ctr = p.counters + 2 * (tile % tiles_mn);
+                        int *ctr = p.counters + 2 * item_mn(tile);
                         if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
                             ctr[1] = 0;
                             __threadfence();
@@ -414,6 +551,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                 }
+                if (row == 0) stamp(p, 7);
                 continue;
             }
 
@@ -600,6 +738,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }   // mi
+            if (row == 0) stamp(p, 7);
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);
         }

@@ -121,7 +121,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         }
         umma_conv::Params p = b.up;
         p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
-        p.workspace = b.d_workspace; p.counters = b.d_counters;
+        p.workspace = b.d_workspace; p.counters = b.d_counters; p.timeline = b.d_timeline;
         if (b.pair) {
             pairconv::Params q = b.pp;
             q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
@@ -551,7 +551,7 @@ int dnnb_net_finalize(dnnb_net *net) {
                 if (encode_map_b(b, &b.map_b_pair_tail, 64)) return 1;
                 net->launches += 1;
             }
-            if (b.up.splits > 1) {
+            if (b.up.splits > 1 && !b.up.cluster_splitk) {
                 const size_t ws = (size_t)b.up.splits * b.up.num_m_tiles * (b.umma->key.mt) * umma_conv::kBM * ocp * sizeof(float);
                 const size_t nc = (size_t)b.up.num_m_tiles * b.up.num_n_tiles * 2 * sizeof(int);
                 CK(cudaMalloc(&b.d_workspace, ws));
@@ -1035,6 +1035,9 @@ int dnnb_net_block_info(dnnb_net *net, int block, int *info) {
                : b.family == DNNB_KERNEL_UMMA_ROWPAIR ? b.rp.num_tiles
                : b.pair ? b.pp.num_m_tiles * b.pp.num_n_tiles
                : b.umma ? b.up.num_m_tiles * b.up.num_n_tiles * b.up.splits : 0;
+    info[13] = b.umma && !b.pair ? b.up.splits : 1;
+    info[14] = b.umma && !b.pair && b.up.splits > 1 && b.up.cluster_splitk ? 1 : 0;
+    info[15] = 0;
     return 0;
 }
 
@@ -1122,6 +1125,30 @@ int dnnb_net_knobs(dnnb_net *net, char *buf, int buf_len) {
     return 0;
 }
 
+int dnnb_net_debug_timeline(dnnb_net *net, int block, unsigned long long *host_out, int *ctas) {
+    if (check_net(net, true)) return 1;
+    if (block < 0 || block >= (int)net->blocks.size() || !ctas) return fail("bad block index or argument");
+    Block &b = net->blocks[block];
+    if (!b.umma || b.pair) return fail("block %d does not run the generic tcgen05 kernel", block);
+    DeviceGuard g(net->device);
+    CK(dnnb_sync_streams(net));
+    const size_t bytes = (size_t)b.grid * 8 * sizeof(unsigned long long);
+    if (!host_out) {                         // arm: allocate + clear; graphs recorded without the pointer are dropped
+        if (!b.d_timeline) CK(cudaMalloc(&b.d_timeline, bytes));
+        CK(cudaMemset(b.d_timeline, 0, bytes));
+        for (dnnb_net::GraphSlot &gs : net->graphs) cudaGraphExecDestroy(gs.exec);
+        net->graphs.clear();
+        net->warm_in = nullptr;
+        net->warm_out = nullptr;
+        *ctas = b.grid;
+        return 0;
+    }
+    if (!b.d_timeline) return fail("timeline of block %d was never armed", block);
+    CK(cudaMemcpy(host_out, b.d_timeline, bytes, cudaMemcpyDeviceToHost));
+    *ctas = b.grid;
+    return 0;
+}
+
 int dnnb_net_debug_block_limit(dnnb_net *net, int blocks) {
     if (check_net(net, true)) return 1;
     DeviceGuard g(net->device);
@@ -1145,6 +1172,7 @@ int dnnb_net_destroy(dnnb_net *net) {
         if (b.d_wpack) cudaFree(b.d_wpack);
         if (b.d_workspace) cudaFree(b.d_workspace);
         if (b.d_counters) cudaFree(b.d_counters);
+        if (b.d_timeline) cudaFree(b.d_timeline);
         if (b.d_scale) cudaFree(b.d_scale);
         if (b.d_shift) cudaFree(b.d_shift);
     }

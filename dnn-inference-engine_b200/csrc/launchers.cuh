@@ -21,6 +21,8 @@ namespace {
 // scheduled after every CTA of this grid has started, so the siblings are co-resident either way.
 thread_local bool t_pdl = false;
 
+thread_local unsigned t_cluster = 0;    // > 1: the next launch_ex launches thread-block clusters of this many CTAs
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool coop,
                       Args &&...args) {
@@ -29,8 +31,16 @@ cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, siz
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     unsigned n = 0;
+    if (t_cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = t_cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+        coop = false;        // co-scheduling within a cluster is guaranteed by the hardware
+    }
     if (t_pdl) {
         attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -57,11 +67,35 @@ struct UmmaKey {
     bool stage_out;   // output tile staged in smem (rows that are not 16-byte multiples)
     bool pool1 = false;   // 2x2/1 SAME max-pool fused in the epilogue (im2col tiles overlapping by W + 1 rows)
 };
+typedef int (*UmmaClusterQuery)(int cluster_size);      // how many clusters of that size can be resident at once (0: not launchable)
 struct UmmaEntry {
     UmmaKey key;
     UmmaLauncher launch;
     int stages, smem;
+    UmmaClusterQuery max_clusters;
 };
+
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false>
+int umma_max_clusters(int cluster_size) {
+    using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO, P1>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cluster_size > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cluster_size * 16);
+    cfg.blockDim = dim3(umma_conv::kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false>
 cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
@@ -71,19 +105,34 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
+    if (p.cluster_splitk && p.splits > 1) {
+        static bool np_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (p.splits > 8 && (dev < 0 || dev >= 64 || !np_done[dev])) {       // clusters of 16: beyond the portable size
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) np_done[dev] = true;
+        }
+        t_cluster = (unsigned)p.splits;
+        e = launch_ex(kern, (unsigned)(grid < 0 ? -grid : grid), umma_conv::kThreads, C::SMEM_BYTES, st, false, ma, mb, p);
+        t_cluster = 0;
+        return e;
+    }
     // grid < 0 = split-K: sibling CTAs wait for one another, so the whole grid must be resident
     return launch_ex(kern, (unsigned)(grid < 0 ? -grid : grid), umma_conv::kThreads, C::SMEM_BYTES, st, grid < 0, ma, mb, p);
 }
 
 #define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                              \
     {{BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT, false}, &launch_umma<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>,  \
-     umma_conv::Cfg<BN, SWZ, KBS, MT>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, MT>::SMEM_BYTES}
+     umma_conv::Cfg<BN, SWZ, KBS, MT>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, MT>::SMEM_BYTES,                 \
+     &umma_max_clusters<BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT>}
 #define UMMA_ENTRY_SO(BF16, BN, SWZ, KBS)                                                                  \
     {{BF16, false, BN, SWZ, KBS, true, false, 1, true}, &launch_umma<BF16, false, BN, SWZ, KBS, true, false, 1, true>, \
-     umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES}
+     umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES, nullptr}
 #define UMMA_ENTRY_P1(BF16, OBF, BN)                                                                       \
     {{BF16, OBF, BN, 128, 1, true, false, 1, false, true}, &launch_umma<BF16, OBF, BN, 128, 1, true, false, 1, false, true>, \
-     umma_conv::Cfg<BN, 128, 1, 1, false, true>::STAGES, umma_conv::Cfg<BN, 128, 1, 1, false, true>::SMEM_BYTES}
+     umma_conv::Cfg<BN, 128, 1, 1, false, true>::STAGES, umma_conv::Cfg<BN, 128, 1, 1, false, true>::SMEM_BYTES, nullptr}
 #define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
 
 const UmmaEntry g_umma_table[] = {

@@ -3,6 +3,7 @@
 // activations and weights, and plan_block(), which decides for every conv block of
 // proj3/yolov2tiny.py:30-77 which kernel runs it, with which tiles, and how its tail rows are cut.
 #pragma once
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,7 +65,7 @@ const KnobDef g_knob_defs[] = {
     {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1},
     {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
     {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
-    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_NO_L2_PREFETCH", true, 0, 1},
+    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_NO_L2_PREFETCH", true, 0, 1}, {"DNNB_VERBOSE_PLAN", true, 0, 1},
 };
 
 // Reads the switches.  `active` receives "NAME=value" for every switch that is set to something other than
@@ -185,6 +186,7 @@ struct Block {
     float *d_scale = nullptr, *d_shift = nullptr;
     float *d_workspace = nullptr;               // split-K partial sums, one slab per K slice
     int *d_counters = nullptr;                  // split-K arrival / departure counters per tile (zero between launches)
+    unsigned long long *d_timeline = nullptr;   // debug: per-CTA phase stamps of the generic kernel (dnnb_net_debug_timeline)
     void *d_conv_out = nullptr;                 // conv(+fused pool) output
     void *d_out = nullptr;                      // block output (== d_conv_out unless pool_separate)
     size_t conv_out_elems = 0, out_elems = 0;
@@ -448,7 +450,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 e = find_umma(key);
             }
             const int stride = fuse1 ? umma_conv::kBM - (b.iw + 1) : umma_conv::kBM;
-            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out) {
+            if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out && !kn.latency) {
                 UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
                 key_so.stage_out = true;
                 const UmmaEntry *e_so = find_umma(key_so);
@@ -513,6 +515,20 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                     const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
                     if (sp > kstages / min_stages) sp = kstages / min_stages;
                     if (sp >= 2) p.splits = sp;
+                    // Cluster split-K: the K slices of a tile are the CTAs of one thread-block cluster (2, 4, 8 or 16) and
+                    // the partial sums are reduced through distributed shared memory instead of a workspace in global
+                    // memory guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once.
+                    if (sp >= 2 && !kn.no_cluster_splitk && mt == 1 && !e->key.stage_out && !fuse1 && e->max_clusters) {
+                        int spc = 16;
+                        while (spc > sp) spc /= 2;
+                        if (getenv("DNNB_VERBOSE_PLAN"))
+                            for (int c = 16; c >= 2; --c)
+                                fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, e->max_clusters(c));
+                        while (spc >= 2 && e->max_clusters(spc) < tiles_mn) spc /= 2;
+                        // not at the price of the weight stream's parallelism (8 tiles x clusters of 8 = 64 CTAs stream a
+                        // 13x13x1024 layer twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use
+                        if (spc >= 2 && 4 * spc >= 3 * sp) { p.splits = spc; p.cluster_splitk = 1; }
+                    }
                 }
                 const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;

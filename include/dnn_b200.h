@@ -168,9 +168,11 @@ int dnnb_net_block_output(dnnb_net *net, int block, float *host_out);
  * output is rewritten with identical values. */
 int dnnb_net_debug_prepool(dnnb_net *net, int block, float *host_out);
 
-/* info[0..12] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
+/* info[0..15] = {kernel family, out_h, out_w, out_c, pooled(0/1: pool fused in the conv
  * epilogue), BN tile, swizzle bytes, stages, grid, separate-pool-kernel(0/1), elem bytes of the
- * stored activation, launches per forward, work items (tiles) of the main launch} */
+ * stored activation, launches per forward, work items (tiles) of the main launch, K slices per
+ * output tile (split-K, latency plan; 1 = none), 1 if those slices are the CTAs of one thread-block
+ * cluster reduced through distributed shared memory, reserved} */
 int dnnb_net_block_info(dnnb_net *net, int block, int *info);
 
 /* Times each block's kernels with CUDA events on the network's stream: `iters` timed
@@ -191,6 +193,13 @@ int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
  * forwards at increasing limits gives each block's in-situ share of the batch-1 latency, overlap
  * between programmatically chained kernels included (tools/batch1_probe.py). */
 int dnnb_net_debug_block_limit(dnnb_net *net, int blocks);
+
+/* Debug / measurement: per-CTA phase stamps (%globaltimer, ns) of a block that runs the generic tcgen05 kernel.
+ * host_out == NULL arms the block (later forwards record 8 stamps per CTA: entry, prologue done, predecessor
+ * complete, first operands landed, last MMA issued, accumulator complete, split-K siblings seen, result stored);
+ * host_out != NULL copies [ctas][8] stamps back.  *ctas receives the block's grid size either way.  Where the
+ * micro-seconds of the batch-1 chain go (tools/batch1_timeline.py). */
+int dnnb_net_debug_timeline(dnnb_net *net, int block, unsigned long long *host_out, int *ctas);
 
 int dnnb_net_destroy(dnnb_net *net);
 
