@@ -46,8 +46,10 @@ struct Params {
     int M_total;          // im2col mode: B*H*W
     int m_base;           // im2col mode: first output pixel of this launch (a block may be cut into a main launch
                           // of whole waves and a finer-tiled tail launch over the remaining rows)
-    int m_stride;         // im2col mode: output pixels a 128-row tile advances: 128, or 128 - (W + 1) when the 2x2/1
-                          // SAME pool is fused (POOL1: the last W + 1 rows of a tile are halo, epilogue_pool1.cuh)
+    int m_stride;         // im2col mode: output pixels a 128-row tile advances: 128; with a pool fused through the staging
+                          // area (POOL1, epilogue_pool1.cuh) 128 - (W + 1) for the 2x2/1 SAME pool (the last W + 1 rows of
+                          // a tile are halo) or a whole number of image-row pairs (2kW) for the 2x2/2 pool
+    int pool_stride;      // POOL1: 1 = 2x2/1 SAME pool, 2 = 2x2/2 pool
     const float *scale;   // [num_n_tiles*BN]  gamma / sqrt(var + eps)      (1 when no BN)
     const float *shift;   // [num_n_tiles*BN]  (bias - mean) * scale         (bias when no BN)
     void *out;            // [B, OH, OW, OC]
@@ -128,7 +130,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int BKC = SWZ / ES;            // channels per K-block
     constexpr int MMA_PER_KB = SWZ / 32;     // each MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
     static_assert(!(POOL && IM2COL), "the fused pool needs spatial tiles");
-    constexpr bool kClusterCapable = IM2COL && !POOL && !POOL1 && !STAGE_OUT && MT == 1;     // variants that carry the cluster split-K path
+    constexpr bool kClusterCapable = IM2COL && !POOL && !STAGE_OUT && MT == 1;     // variants that carry the cluster split-K path
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -363,7 +365,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (row == 0) stamp(p, 6);
                     const int rank = (int)ptx::cluster_ctarank();     // == item_split(tile)
                     const int cw = BN / p.splits;                     // strip width in floats: a multiple of 4 (splits <= 16 <= BN / 8)
-                    const int c4n = cw >> 2;                          // 16-byte units per row of the strip
+                    // the strip goes through in sub-strips of at most 32 columns (the width of the pool staging area)
+                    for (int sub = 0; sub < cw; sub += 32) {
+                    const int sw = cw - sub < 32 ? cw - sub : 32;
+                    const int c4n = sw >> 2;                          // 16-byte units per row of the sub-strip
                     // item = (row, 16-byte unit) of the strip, consecutive threads = consecutive units of a row: a warp's remote
                     // load is then a few whole 128-byte runs of one peer's shared memory (one scattered 16 bytes per lane ran
                     // at a tenth of the speed)
@@ -371,7 +376,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const int r = item / c4n, c4 = (item - r * c4n) * 4;
                         const int m = p.m_base + m_tile * p.m_stride + r;
                         if (m >= p.M_total) break;                    // rows ascend with the item index
-                        const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + c4) * 4;
+                        const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + sub + c4) * 4;
                         float4 t4[16];
 #pragma unroll
                         for (int peer = 0; peer < 16; ++peer) {       // all peers' loads in flight together, then summed in rank order
@@ -386,7 +391,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             if (peer < p.splits) { sum.x += t4[peer].x; sum.y += t4[peer].y; sum.z += t4[peer].z; sum.w += t4[peer].w; }
                         }
                         float v4[4] = {sum.x, sum.y, sum.z, sum.w};
-                        const int col = n_tile * BN + rank * cw + c4;
+                        const int col = n_tile * BN + rank * cw + sub + c4;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
@@ -395,7 +400,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             else if (p.round_tf32) y = ptx::round_tf32(y);
                             v4[e] = y;
                         }
-                        if constexpr (OUT_BF16) {
+                        if constexpr (POOL1) {
+                            // the strip's rows all live in this CTA: stage the activated values, pool below
+                            if (p.prepool != nullptr && r < p.m_stride) {
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.OC) p.prepool[(size_t)m * p.OC + col + e] = v4[e];
+                            }
+                            pool1::sts4(ptx::smem_u32(s_out) + (uint32_t)(r * pool1::kPitch + c4) * 4, v4[0], v4[1], v4[2], v4[3]);
+                        } else if constexpr (OUT_BF16) {
                             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
@@ -410,6 +422,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             }
                         }
                     }
+                    if constexpr (POOL1) {
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        const int m0 = p.m_base + m_tile * p.m_stride;
+                        if (p.pool_stride == 2)
+                            pool1::emit_s2<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.W, p.OC,
+                                                     n_tile * BN + rank * cw + sub, sw, p.out);
+                        else
+                            pool1::emit_s1<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.H, p.OC,
+                                                     n_tile * BN + rank * cw + sub, sw, p.out);
+                        asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging area is rewritten by the next sub-strip
+                    }
+                    }   // sub
                     if (row == 0) stamp(p, 7);
                     ptx::cluster_sync_all();                          // #2: nobody reads this CTA's shared memory any more
                     continue;
@@ -610,6 +634,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
                     if constexpr (POOL1) {
                         pool1::dump_prepool(v, (int)out_pix, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
+                        if (p.pool_stride == 2)
+                            pool1::store_chunk_s2<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
+                                                            p.m_stride, p.M_total, p.W, p.OC, col0, p.out);
+                        else
                         pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
                                                      p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool);
                     } else if constexpr (POOL) {

@@ -77,6 +77,76 @@ __device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[3
     (void)prepool;
 }
 
+// The 2x2 stride-2 pool over an im2col tile that is whole PAIRS of image rows (m_stride = 2k W pixels, W even;
+// small batches under the latency plan, where spatial tiles would be mostly padding): pooled pixel (pr, pc) of the
+// tile is the maximum of tile rows 2 pr W + 2 pc + {0, 1, W, W + 1}.  `s_stage` holds [128][kPitch] activated values
+// of `ncols` <= 32 channels starting at channel col0; the caller has synchronised after filling it.  Image heights
+// are even, so a pair of flattened rows never straddles two images and the pooled tensor [B, H/2, W/2, OC] is simply
+// flattened-row / 2.
+template <bool OUT_BF16>
+__device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane, int m0, int m_stride, int M_total, int W,
+                                        int OC, int col0, int ncols, void *out) {
+    const int half_w = W >> 1;
+    const int n_pooled = m_stride >> 2;
+    const int col = col0 + lane;
+    if (lane >= ncols || col >= OC) return;
+    const int orow0 = (m0 / W) >> 1;                  // pooled flattened row of the tile's first row pair
+    for (int q = quarter; q < n_pooled; q += 4) {
+        const int pr = q / half_w, pc = q - pr * half_w;
+        const int r00 = 2 * pr * W + 2 * pc;
+        if (m0 + r00 + W + 1 >= M_total) break;       // pooled pixels ascend with q: everything further lies past the batch
+        const uint32_t a = s_stage + (uint32_t)(r00 * kPitch + lane) * 4;
+        const float v = fmaxf(fmaxf(lds(a), lds(a + kPitch * 4)), fmaxf(lds(a + W * kPitch * 4), lds(a + (W + 1) * kPitch * 4)));
+        const size_t o = ((size_t)(orow0 + pr) * half_w + pc) * OC + col;
+        if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[o] = __float2bfloat16_rn(v);
+        else static_cast<float *>(out)[o] = v;
+    }
+}
+
+// The stride-1 window walk on an already filled staging area (`ncols` <= 32 channels): second half of store_chunk.
+template <bool OUT_BF16>
+__device__ __forceinline__ void emit_s1(uint32_t s_stage, int quarter, int lane, int m0, int m_stride, int M_total, int H,
+                                        int OC, int col0, int ncols, void *out) {
+    const int r0 = quarter * 32;
+    constexpr int kRows = 32 + kHalo + 1;
+    float x[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) x[i] = lds(s_stage + (uint32_t)(min(r0 + i, 127) * kPitch + lane) * 4);
+    const int m = m0 + r0;
+    const int hw = m % (H * kW);
+    int h = hw / kW, w = hw - h * kW;
+    int wi = w;
+#pragma unroll
+    for (int i = 0; i < 32 + kW; ++i) {
+        if (wi + 1 < kW) x[i] = fmaxf(x[i], x[i + 1]);
+        if (++wi == kW) wi = 0;
+    }
+    const int col = col0 + lane;
+    if (lane >= ncols || col >= OC) return;
+    const int n_rows = min(min(32, m_stride - r0), M_total - m);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i < n_rows) {
+            const float a = (h + 1 < H) ? fmaxf(x[i], x[i + kW]) : x[i];
+            if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[(size_t)(m + i) * OC + col] = __float2bfloat16_rn(a);
+            else static_cast<float *>(out)[(size_t)(m + i) * OC + col] = a;
+        }
+        if (++w == kW) { w = 0; if (++h == H) h = 0; }
+    }
+}
+
+// One 32-column chunk through the staging area with either pool (stride 1: store_chunk above; stride 2 here).
+template <bool OUT_BF16>
+__device__ __forceinline__ void store_chunk_s2(uint32_t s_stage, const float (&v)[32], int quarter, int lane, int m0, int m_stride,
+                                               int M_total, int W, int OC, int col0, void *out) {
+    const uint32_t mine = s_stage + (uint32_t)(quarter * 32 + lane) * (kPitch * 4);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) sts4(mine + 4 * j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    emit_s2<OUT_BF16>(s_stage, quarter, lane, m0, m_stride, M_total, W, OC, col0, 32, out);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // Debug variant of the first half: dumps this thread's own row of the chunk (all 128 tile rows are written by
 // somebody: rows [0, m_stride) belong to this tile, the halo rows to the next one, which writes the same values).
 __device__ __forceinline__ void dump_prepool(const float (&v)[32], int m, int M_total, int owned, int OC, int col0,

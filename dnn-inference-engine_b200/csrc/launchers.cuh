@@ -132,7 +132,8 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
      umma_conv::Cfg<BN, SWZ, KBS, 1, true>::STAGES, umma_conv::Cfg<BN, SWZ, KBS, 1, true>::SMEM_BYTES, nullptr}
 #define UMMA_ENTRY_P1(BF16, OBF, BN)                                                                       \
     {{BF16, OBF, BN, 128, 1, true, false, 1, false, true}, &launch_umma<BF16, OBF, BN, 128, 1, true, false, 1, false, true>, \
-     umma_conv::Cfg<BN, 128, 1, 1, false, true>::STAGES, umma_conv::Cfg<BN, 128, 1, 1, false, true>::SMEM_BYTES, nullptr}
+     umma_conv::Cfg<BN, 128, 1, 1, false, true>::STAGES, umma_conv::Cfg<BN, 128, 1, 1, false, true>::SMEM_BYTES,  \
+     &umma_max_clusters<BF16, OBF, BN, 128, 1, true, false, 1, false, true>}
 #define UMMA_ENTRY(BF16, OBF, BN, SWZ, KBS, I2C, POOL) UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, 1)
 
 const UmmaEntry g_umma_table[] = {

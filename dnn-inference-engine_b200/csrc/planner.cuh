@@ -46,6 +46,7 @@ struct Knobs {
     bool no_cluster_splitk = false;  // DNNB_NO_CLUSTER_SPLITK latency plan: split-K through the global workspace, not cluster DSMEM
     bool no_tma_store = false;       // DNNB_NO_TMA_STORE     epilogues store with per-thread st.global instead of bulk copies
     bool no_l2_prefetch = false;     // DNNB_NO_L2_PREFETCH   latency plan: no L2 prefetch of the later blocks' weights
+    bool verbose_plan = false;       // DNNB_VERBOSE_PLAN     print planning decisions to stderr
 };
 
 // Every DNNB_* variable the library understands.  Anything else that starts with DNNB_ is a typo or a stale
@@ -136,6 +137,7 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.no_cluster_splitk = value("DNNB_NO_CLUSTER_SPLITK", 0) != 0;
     k.no_tma_store = value("DNNB_NO_TMA_STORE", 0) != 0;
     k.no_l2_prefetch = value("DNNB_NO_L2_PREFETCH", 0) != 0;
+    k.verbose_plan = value("DNNB_VERBOSE_PLAN", 0) != 0;
     return bad ? 1 : 0;
 }
 
@@ -437,19 +439,63 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // take the im2col tiling (consecutive pixels) and a separate pool kernel instead
                 if (fuse && net->B * 2 <= nb && nb > kn.lat_fuse_nb && kn.latency) fuse = false;
             }
-            // the 2x2 stride-1 SAME pool of block 5 fused into the im2col epilogue: tiles advance by 128 - (W + 1)
-            // output pixels, the last W + 1 rows of each tile are halo (epilogue_pool1.cuh).  Not with split-K.
-            bool fuse1 = !fuse && b.pool_k == 2 && b.pool_s == 1 && b.pool_same && b.oh == b.ch && b.ow == b.cw &&
-                         b.ppt == 0 && b.ppl == 0 && b.iw == pool1::kW && swz == 128 && kbs == 1 && b.oc % 4 == 0 &&
-                         !kn.no_pool1_fusion && !kn.latency;
-            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false, fuse1};
-            const UmmaEntry *e = find_umma(key);
-            if (!e && fuse1) {
-                fuse1 = false;
-                key.pool1 = false;
-                e = find_umma(key);
+            // A pool fused into the IM2COL epilogue (epilogue_pool1.cuh), for blocks whose tiles are runs of consecutive
+            // pixels: (1) the 2x2 stride-1 SAME pool of block 5 -- tiles advance by 128 - (W + 1) output pixels, the last
+            // W + 1 rows of each tile are halo; (2) a 2x2/2 pool when the spatial tiling was given up (small batches under
+            // the latency plan) -- tiles are whole pairs of image rows, 2kW <= 128 pixels.  Split-K is compatible only in
+            // its cluster form (all rows of a column strip end up in one CTA), so the split is decided first.
+            const int total_kstages = total_kb / kbs;
+            auto decide_split = [&](const UmmaEntry *ent, int tiles_mn, int mt_, int &splits, int &cluster) {
+                splits = 1;
+                cluster = 0;
+                // Splitting costs a few us (partials exchanged, sibling wait, reduction) and a CTA streams one ring of smem
+                // stages per ~2 us round trip, so a K loop of up to three ring passes stays whole (measured, batch 1:
+                // block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
+                const bool long_k = total_kstages > 3 * ent->stages || kn.split_min_stages > 0;
+                if (fuse || !(tiles_mn * 2 <= net->num_sms && total_kstages >= 8 && long_k && kn.latency)) return;
+                int sp = net->num_sms / tiles_mn;
+                const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
+                if (sp > total_kstages / min_stages) sp = total_kstages / min_stages;
+                if (sp < 2) return;
+                splits = sp;
+                // Cluster split-K: the K slices of a tile are the CTAs of one thread-block cluster (2, 4, 8 or 16) and the
+                // partial sums are reduced through distributed shared memory instead of a workspace in global memory
+                // guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once -- and not at the
+                // price of the weight stream's parallelism (8 tiles x clusters of 8 = 64 CTAs stream a 13x13x1024 layer
+                // twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use.
+                if (kn.no_cluster_splitk || mt_ != 1 || ent->key.stage_out || !ent->max_clusters) return;
+                int spc = 16;
+                while (spc > sp) spc /= 2;
+                if (kn.verbose_plan)
+                    for (int c = 16; c >= 2; --c)
+                        fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, ent->max_clusters(c));
+                while (spc >= 2 && ent->max_clusters(spc) < tiles_mn) spc /= 2;
+                if (spc >= 2 && 4 * spc >= 3 * sp) { splits = spc; cluster = 1; }
+            };
+            int ipool = 0;           // 0 none, 1 = 2x2/1 SAME, 2 = 2x2/2
+            int stride = umma_conv::kBM;
+            if (!fuse && b.pool_k == 2 && swz == 128 && kbs == 1 && b.oc % 4 == 0 && !kn.no_pool1_fusion) {
+                if (b.pool_s == 1 && b.pool_same && b.oh == b.ch && b.ow == b.cw && b.ppt == 0 && b.ppl == 0 && b.iw == pool1::kW) {
+                    ipool = 1;
+                    stride = umma_conv::kBM - (b.iw + 1);
+                } else if (b.pool_s == 2 && b.ih % 2 == 0 && b.iw % 2 == 0 && 2 * b.iw <= umma_conv::kBM) {
+                    ipool = 2;
+                    stride = umma_conv::kBM / (2 * b.iw) * (2 * b.iw);
+                }
             }
-            const int stride = fuse1 ? umma_conv::kBM - (b.iw + 1) : umma_conv::kBM;
+            UmmaKey key{in_bf16, b.out_bf16, bn, swz, kbs, !fuse, fuse, 1, false, ipool != 0};
+            const UmmaEntry *e = find_umma(key);
+            if (ipool) {
+                int sp = 1, cl = 0;
+                if (e) decide_split(e, (int)(((long)net->B * b.ih * b.iw + stride - 1) / stride) * (ocp / bn), 1, sp, cl);
+                if (!e || (sp > 1 && !cl)) {          // no such kernel, or a workspace split-K: the pool stays a kernel of its own
+                    ipool = 0;
+                    stride = umma_conv::kBM;
+                    key.pool1 = false;
+                    e = find_umma(key);
+                }
+            }
+            const bool fuse1 = ipool != 0;
             if (e && !fuse && !b.out_bf16 && ocp == bn && b.oc % 4 != 0 && !kn.no_stage_out && !kn.latency) {
                 UmmaKey key_so = key;            // narrow odd rows: stage the output tile in smem
                 key_so.stage_out = true;
@@ -504,32 +550,8 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 p.tma_store = kn.no_tma_store ? 0 : 1;
                 // split-K when the output tiles alone cannot occupy the SMs (small batches)
                 const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
-                const int kstages = total_kb / kbs;
-                p.splits = 1;
-                // Splitting costs ~7 us (partials through L2, sibling wait, reduction) and a CTA streams one ring
-                // of smem stages per ~2 us round trip, so a K loop of up to three ring passes stays whole
-                // (measured, batch 1: block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
-                const bool long_k = kstages > 3 * e->stages || kn.split_min_stages > 0;
-                if (!fuse && tiles_mn * 2 <= net->num_sms && kstages >= 8 && long_k && kn.latency) {
-                    int sp = net->num_sms / tiles_mn;
-                    const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
-                    if (sp > kstages / min_stages) sp = kstages / min_stages;
-                    if (sp >= 2) p.splits = sp;
-                    // Cluster split-K: the K slices of a tile are the CTAs of one thread-block cluster (2, 4, 8 or 16) and
-                    // the partial sums are reduced through distributed shared memory instead of a workspace in global
-                    // memory guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once.
-                    if (sp >= 2 && !kn.no_cluster_splitk && mt == 1 && !e->key.stage_out && !fuse1 && e->max_clusters) {
-                        int spc = 16;
-                        while (spc > sp) spc /= 2;
-                        if (getenv("DNNB_VERBOSE_PLAN"))
-                            for (int c = 16; c >= 2; --c)
-                                fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, e->max_clusters(c));
-                        while (spc >= 2 && e->max_clusters(spc) < tiles_mn) spc /= 2;
-                        // not at the price of the weight stream's parallelism (8 tiles x clusters of 8 = 64 CTAs stream a
-                        // 13x13x1024 layer twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use
-                        if (spc >= 2 && 4 * spc >= 3 * sp) { p.splits = spc; p.cluster_splitk = 1; }
-                    }
-                }
+                decide_split(e, tiles_mn, mt, p.splits, p.cluster_splitk);
+                p.pool_stride = ipool;
                 const int tiles = tiles_mn * p.splits;       // split-K: one resident CTA per work item (tiles <= SMs)
                 b.grid = tiles < net->num_sms ? tiles : net->num_sms;
                 // CTA pairs (conv_pair.cuh, tcgen05.mma.cta_group::2) for the big im2col blocks: a third to a
@@ -538,7 +560,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 b.pair = nullptr;
                 b.umma_tail = nullptr;
                 const int sms = net->num_sms;
-                if (!fuse && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
+                if (!fuse && ipool != 2 && p.splits == 1 && bn == 256 && swz == 128 && kbs == 1 && !e->key.stage_out && ocp == b.oc &&
                     sms % 2 == 0 && !kn.no_pair) {
                     // measured (batch 512, whole step): MT = 1 everywhere 84.4 k img/s, MT = 2 for K >= 4096 83.7 k,
                     // MT = 2 everywhere 82.8 k, no pairs 82.5 k -- two accumulator stages and six smem stages are

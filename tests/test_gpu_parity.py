@@ -230,6 +230,42 @@ def test_fused_stride1_pool_picks_the_reference_maximum(oracle_libs, monkeypatch
     sep.close()
 
 
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("layer,batch", [(3, 1), (4, 1), (5, 1), (4, 3), (5, 2)])
+def test_latency_plan_pools_inside_the_conv_kernels(oracle_libs, layer, batch, precision):
+    """Small batches under the latency plan give up the spatial tiles (they would be mostly padding) for runs of
+    consecutive pixels; the pools are fused all the same -- 2x2/2 over tiles that are whole pairs of image rows
+    (blocks 3, 4), 2x2/1 over tiles overlapping by W + 1 rows (block 5) -- including behind the cluster split-K
+    reduction, where every CTA ends up with all rows of a column strip.  Operator-local identity as above."""
+    w = make_weights(60 + layer, negative_gamma=(batch > 1))[layer]
+    x = np.random.default_rng(70 + layer + batch).standard_normal((batch, HW[layer], HW[layer], CHANNELS[layer])).astype(np.float32)
+    nxt = make_weights(61)[layer + 1]
+    net = _lib.Net(x.shape, [_layer_spec(layer, w), _layer_spec(layer + 1, nxt)], precision=precision, latency=True)
+    net.forward(x)
+    info = net.block_info(0)
+    print("layer %d batch %d %s: %s" % (layer, batch, precision, info))
+    assert info["kernel"] == "umma_im2col"
+    if batch == 1:
+        assert info["pool_fused"] and not info["pool_separate"] and info["launches"] == 1
+        assert info["splits"] == 1 or info["cluster_splitk"]
+        if layer >= 4:
+            assert info["splits"] > 1                  # the weight stream is spread over more CTAs than there are tiles
+    else:       # the planner may prefer the workspace split-K (more CTAs), whose pool is a kernel of its own
+        assert info["pool_fused"] != info["pool_separate"] and (info["pool_fused"] or not info["cluster_splitk"])
+    pooled = net.block_output(0)
+    k, st = POOLS[layer]
+    if info["pool_fused"]:
+        prepool = net.debug_prepool(0, (HW[layer], HW[layer]))
+        np.testing.assert_array_equal(net.block_output(0), pooled)
+        ref, _ = chain.pool_argmax(prepool, k, st)
+        np.testing.assert_array_equal(pooled, ref)
+        assert normalised_error(prepool, _oracle_block(layer, w, x, pool=False)) < (2e-3 if precision == "tf32" else 1.2e-2)
+    assert normalised_error(pooled, _oracle_block(layer, w, x)) < (2e-3 if precision == "tf32" else 1.2e-2)
+    again = net.forward(x).copy()
+    np.testing.assert_array_equal(net.forward(x), again)          # reproducible run to run
+    net.close()
+
+
 # ------------------------------------------------------------------------------- end to end
 def _yolo_engine(batch, precision, wseed=0, debug=False):
     g = dnn_b200.DnnGraphBuilder()
