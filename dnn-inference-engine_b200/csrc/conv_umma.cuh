@@ -58,6 +58,7 @@ struct Params {
     int round_tf32;       // fp32 storage only: round stored values to TF32 (they feed a kind::tf32 block)
     float *prepool;       // debug (fused pool only): also dump the pre-pool activations [B,H,W,OC] fp32
     int tma_store;        // STAGE_OUT: write the staged rows with bulk async copies (0: per-lane stores; DNNB_NO_TMA_STORE)
+    int pool_first;       // POOL: every scale[c] > 0 -> the launcher picks the POOL_FIRST instantiation
     // split-K (small batches: too few output tiles to fill the SMs, weights dominate the traffic):
     // `splits` CTAs share one output tile.  Each stores the partial sums of its K slice to its own
     // slab of `workspace`, bumps `counters[tile]` and waits until all `splits` slabs are there; then
@@ -117,13 +118,14 @@ struct Cfg {
 };
 
 template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT = 1, bool STAGE_OUT = false,
-          bool POOL1 = false>
+          bool POOL1 = false, bool POOL_FIRST = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const Params p) {
     using C = Cfg<BN, SWZ, KBS, MT, STAGE_OUT, POOL1>;
     static_assert(!STAGE_OUT || (IM2COL && !POOL && !OUT_BF16 && MT == 1), "staged output: plain fp32 im2col tiles only");
     static_assert(!POOL1 || (IM2COL && !POOL && !STAGE_OUT), "the fused 2x2/1 pool needs im2col tiles");
+    static_assert(!POOL_FIRST || POOL, "pool-first is a variant of the fused 2x2/2 pool");
     constexpr int STAGES = C::STAGES;
     constexpr int ACC = C::ACC_STAGES;
     constexpr int ES = BF16 ? 2 : 4;
@@ -609,6 +611,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     ptx::tmem_ld_wait();
                     const int col0 = n_tile * BN + chunk * 32;
                     float v[32];
+                    if constexpr (POOL_FIRST) {
+                        // every scale > 0: scale/shift, LeakyReLU and rounding are monotone, so the window maximum of the raw
+                        // accumulators is taken first and one value is activated instead of four (bit-identical)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
@@ -631,6 +639,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
                     }
+                    }
 
                     if constexpr (POOL1) {
                         pool1::dump_prepool(v, (int)out_pix, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
@@ -641,10 +650,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
                                                      p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool);
                     } else if constexpr (POOL) {
-                        if (p.prepool != nullptr && valid) {
+                        if constexpr (!POOL_FIRST) {      // debug dump of the pooled-over activations (the host selects this variant for it)
+                            if (p.prepool != nullptr && valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.OC) p.prepool[pre_pix * p.OC + col0 + j] = v[j];
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < p.OC) p.prepool[pre_pix * p.OC + col0 + j] = v[j];
+                            }
                         }
                         // butterfly 2x2 max over lanes (w^1, then h^1 = lane ^ tw); each lane ends up
                         // with 8 of the 32 columns of its window: 16*(w&1) + 8*(h&1) + [0,8)
@@ -665,6 +676,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             r8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, p.tw));
                         }
                         const int col = col0 + (wodd ? 16 : 0) + (hodd ? 8 : 0);
+                        if constexpr (POOL_FIRST) {
+                            const float4 sca = *reinterpret_cast<const float4 *>(s_scale + col), scb = *reinterpret_cast<const float4 *>(s_scale + col + 4);
+                            const float4 sha = *reinterpret_cast<const float4 *>(s_shift + col), shb = *reinterpret_cast<const float4 *>(s_shift + col + 4);
+                            const float sc8[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+                            const float sh8[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float y = fmaf(r8[j], sc8[j], sh8[j]);
+                                if (p.leaky) y = fmaxf(y, 0.1f * y);
+                                if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                                else if (p.round_tf32) y = ptx::round_tf32(y);
+                                r8[j] = y;
+                            }
+                        }
                         if (valid && col < p.OC) {
                             if constexpr (OUT_BF16) {
                                 __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col;

@@ -97,11 +97,11 @@ int umma_max_clusters(int cluster_size) {
     return n;
 }
 
-template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false>
-cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
-                        cudaStream_t st) {
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false, bool PF = false>
+cudaError_t launch_umma_t(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
+                          cudaStream_t st) {
     using C = umma_conv::Cfg<BN, SWZ, KBS, MT, SO, P1>;
-    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1>;
+    auto kern = umma_conv::conv_umma_kernel<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1, PF>;
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
@@ -121,6 +121,16 @@ cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma
     }
     // grid < 0 = split-K: sibling CTAs wait for one another, so the whole grid must be resident
     return launch_ex(kern, (unsigned)(grid < 0 ? -grid : grid), umma_conv::kThreads, C::SMEM_BYTES, st, grid < 0, ma, mb, p);
+}
+
+template <bool BF16, bool OUT_BF16, int BN, int SWZ, int KBS, bool IM2COL, bool POOL, int MT, bool SO = false, bool P1 = false>
+cudaError_t launch_umma(const CUtensorMap &ma, const CUtensorMap &mb, const umma_conv::Params &p, int grid,
+                        cudaStream_t st) {
+    if constexpr (POOL) {        // the fused 2x2/2 pool has a pool-first instantiation for all-positive scales
+        if (p.pool_first && p.prepool == nullptr)
+            return launch_umma_t<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1, true>(ma, mb, p, grid, st);
+    }
+    return launch_umma_t<BF16, OUT_BF16, BN, SWZ, KBS, IM2COL, POOL, MT, SO, P1, false>(ma, mb, p, grid, st);
 }
 
 #define UMMA_ENTRY_MT(BF16, OBF, BN, SWZ, KBS, I2C, POOL, MT)                                              \

@@ -548,6 +548,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 p.leaky = b.leaky;
                 p.round_tf32 = b.round_tf32;
                 p.tma_store = kn.no_tma_store ? 0 : 1;
+                p.pool_first = fuse && all_scales_positive(b) && !kn.no_pool_first ? 1 : 0;
                 // split-K when the output tiles alone cannot occupy the SMs (small batches)
                 const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
                 decide_split(e, tiles_mn, mt, p.splits, p.cluster_splitk);
