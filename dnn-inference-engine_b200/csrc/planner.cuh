@@ -36,7 +36,8 @@ struct Knobs {
     bool no_pair = false;            // DNNB_NO_PAIR          no CTA-pair kernel
     int pair_mt = 1;                 // DNNB_PAIR_MT=2        512 x 256 pair tiles
     int pair_min_tiles = -1;         // DNNB_PAIR_MIN_TILES   pair tiles needed to use the pair kernel (default: two waves)
-    bool pair_no_tail = false;       // DNNB_PAIR_NO_TAIL     pairs also run the partial last wave
+    bool pair_no_tail = false;       // DNNB_PAIR_NO_TAIL     pairs also run the partial last wave (no tail launches at all)
+    bool pair_force_tail = false;    // DNNB_PAIR_FORCE_TAIL  tail launches also behind short K loops (tests)
     bool no_pair_tail = false;       // DNNB_NO_PAIR_TAIL     rows past the full waves go to the single-CTA kernel only
     bool no_tail = false;            // DNNB_NO_TAIL          no main/tail cut of wave-quantised 256 x 256 blocks
     int lat_fuse_nb = 0;             // DNNB_LAT_FUSE_NB      latency plan: keep fused spatial tiles up to this many images
@@ -63,7 +64,7 @@ const KnobDef g_knob_defs[] = {
     {"DNNB_NO_ROWPAIR", true, 0, 1},       {"DNNB_ROWPAIR_LINEAR", true, 0, 1},  {"DNNB_NO_ROWPAIR_LINEAR", true, 0, 1},
     {"DNNB_ROWPAIR_MAX_TR", false, 2, 8},  {"DNNB_NO_POOL_FIRST", true, 0, 1},   {"DNNB_NO_STAGE_OUT", true, 0, 1},
     {"DNNB_NO_MT2", true, 0, 1},           {"DNNB_MT2_MASK", false, 0, 1 << 20}, {"DNNB_NO_PAIR", true, 0, 1},
-    {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1},
+    {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1}, {"DNNB_PAIR_FORCE_TAIL", true, 0, 1},
     {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
     {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
     {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_NO_L2_PREFETCH", true, 0, 1}, {"DNNB_VERBOSE_PLAN", true, 0, 1},
@@ -128,6 +129,7 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.pair_mt = value("DNNB_PAIR_MT", 1);
     k.pair_min_tiles = getenv("DNNB_PAIR_MIN_TILES") ? value("DNNB_PAIR_MIN_TILES", -1) : -1;
     k.pair_no_tail = value("DNNB_PAIR_NO_TAIL", 0) != 0;
+    k.pair_force_tail = value("DNNB_PAIR_FORCE_TAIL", 0) != 0;
     k.no_pair_tail = value("DNNB_NO_PAIR_TAIL", 0) != 0;
     k.no_tail = value("DNNB_NO_TAIL", 0) != 0;
     k.lat_fuse_nb = value("DNNB_LAT_FUSE_NB", 0);
@@ -572,13 +574,18 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                     const UmmaEntry *et = find_umma(kt);
                     const int pairs = sms / 2;
                     const int rows_per = 2 * pmt * stride;
-                    const int m_all = p.M_total / rows_per;                 // whole pair tiles
+                    // A tail launch costs a launch gap plus one whole K loop however few tiles it has.  Behind the long K loops of
+                    // the 13x13x512/1024 blocks (a wave of pair tiles takes 100-200 us) that is cheaper than a mostly empty
+                    // last wave; behind a short one (block 5: 72 K blocks, 25 us per wave; its two tails measured 78 us for
+                    // 2.4 % of the rows) it is not: there the pairs take everything, the last tile ragged.
+                    const bool short_k = ((long)b.kh * b.kw * b.ic < 4096 && !kn.pair_force_tail) || kn.pair_no_tail;
+                    const int m_all = short_k ? (p.M_total + rows_per - 1) / rows_per : p.M_total / rows_per;      // pair tiles (whole ones when tails follow)
                     const int tiles_p = m_all * p.num_n_tiles;
                     const int min_tiles = kn.pair_min_tiles >= 0 ? kn.pair_min_tiles : 2 * pairs;
                     if (pe && et && tiles_p >= min_tiles && tiles_p > 0) {
                         // stop at the last full wave when the partial one would be less than half full
                         int main_m = m_all;
-                        if (tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs && !kn.pair_no_tail) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
+                        if (!short_k && tiles_p > pairs && tiles_p % pairs != 0 && (tiles_p % pairs) * 2 < pairs) main_m = (tiles_p / pairs) * pairs / p.num_n_tiles;
                         b.pair = pe;
                         pairconv::Params &q = b.pp;
                         q = pairconv::Params{};
@@ -590,7 +597,7 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         q.leaky = b.leaky; q.round_tf32 = b.round_tf32;
                         const int t = main_m * p.num_n_tiles;
                         b.grid = 2 * (t < pairs ? t : pairs);
-                        int rows_done = main_m * rows_per;
+                        int rows_done = main_m * rows_per < p.M_total ? main_m * rows_per : p.M_total;
                         // whole pair tiles past the full waves: pairs again, in 256 x 128 tiles so that they
                         // spread over twice as many pairs (block 7: 20 tiles -> 40 of the 74 pairs, 100 -> 50 us)
                         b.pair_tail = nullptr;
