@@ -94,6 +94,7 @@ struct Params {
     int pool_first;      // every scale[c] > 0: scale/shift, LeakyReLU and rounding are then monotone, so the
                          // epilogue pools the raw accumulators and activates one value instead of four
     float *prepool;      // debug: also dump the pre-pool activations [B,H,W,16] fp32
+    size_t out_elems;    // extent of `out` in elements (checked by -DDNNB_BOUNDS builds)
 };
 
 template <bool BF16, bool OUT_BF16, bool IN_U8 = false>
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                     if (valid) {
                         const size_t pix = ((size_t)n * OH + (orow >> 1)) * OW + (w >> 1);
                         if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + pix * 16 + (odd ? 8 : 0);
+                            __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 1);
                             __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
                             __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
                             uint4 pk;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
                             pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
                             *reinterpret_cast<uint4 *>(o) = pk;
                         } else {
-                            float *o = static_cast<float *>(p.out) + pix * 16 + (odd ? 8 : 0);
+                            float *o = ptx::out_at<float>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 2);
                             *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
                             *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
                         }

@@ -46,6 +46,7 @@ struct Params {
     const float *shift;
     void *out;
     int leaky, round_tf32;
+    size_t out_elems;         // extent of `out` in elements (checked by -DDNNB_BOUNDS builds)
 };
 
 // kBN = output channels per pair tile (256; 128 for the tail launch over a block's last rows, so that
@@ -233,12 +234,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                         pool1::dump_prepool(v, m, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
                         pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_stage), v, quarter, lane, m_first, p.m_stride, p.M_total, p.H,
-                                                     p.OC, col0, p.out, p.prepool);
+                                                     p.OC, col0, p.out, p.prepool, p.out_elems);
                         continue;
                     }
                     if (!valid) continue;
                     if constexpr (OUT_BF16) {
-                        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col0;
+                        __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, (size_t)m * p.OC + col0, min(32, p.OC - col0), p.out_elems, 3);
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             if (col0 + j < p.OC) {
@@ -259,7 +260,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
                         }
-                        float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col0;
+                        float *o = ptx::out_at<float>(p.out, (size_t)m * p.OC + col0, min(32, p.OC - col0), p.out_elems, 4);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             if (col0 + j < p.OC)

@@ -55,6 +55,7 @@ struct Params {
     int leaky, round_tf32;
     int pool_first;       // every scale[c] > 0: pool the raw accumulators, then activate one value instead of four
     float *prepool;       // debug: also dump the pre-pool activations [B,H,W,OC] fp32
+    size_t out_elems;     // extent of `out` in elements (checked by -DDNNB_BOUNDS builds)
 };
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
@@ -331,9 +332,9 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             uint4 pk;
                             pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
                             pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                            *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(p.out) + off) = pk;
+                            *reinterpret_cast<uint4 *>(ptx::out_at<__nv_bfloat16>(p.out, off, 8, p.out_elems, 5)) = pk;
                         } else {
-                            float *o = static_cast<float *>(p.out) + off;
+                            float *o = ptx::out_at<float>(p.out, off, 8, p.out_elems, 6);
                             *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
                             *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
                         }

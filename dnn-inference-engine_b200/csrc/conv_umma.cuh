@@ -81,6 +81,7 @@ struct Params {
     // (griddepcontrol.wait returned), 3 first operands landed, 4 last MMA issued, 5 accumulator complete, 6 partial tile
     // parked / workspace written and all siblings seen, 7 result stored.  NULL in production.
     unsigned long long *timeline;
+    size_t out_elems;     // extent of `out` in elements (checked by -DDNNB_BOUNDS builds)
 };
 
 __device__ __forceinline__ void stamp(const Params &p, int slot) {
@@ -410,12 +411,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             }
                             pool1::sts4(ptx::smem_u32(s_out) + (uint32_t)(r * pool1::kPitch + c4) * 4, v4[0], v4[1], v4[2], v4[3]);
                         } else if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+                            __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 7);
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
                         } else {
-                            float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                            float *o = ptx::out_at<float>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 8);
                             if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
                             else {
 #pragma unroll
@@ -429,10 +430,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const int m0 = p.m_base + m_tile * p.m_stride;
                         if (p.pool_stride == 2)
                             pool1::emit_s2<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.W, p.OC,
-                                                     n_tile * BN + rank * cw + sub, sw, p.out);
+                                                     n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
                         else
                             pool1::emit_s1<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.H, p.OC,
-                                                     n_tile * BN + rank * cw + sub, sw, p.out);
+                                                     n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
                         asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging area is rewritten by the next sub-strip
                     }
                     }   // sub
@@ -563,12 +564,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         v4[e] = y;
                     }
                     if constexpr (OUT_BF16) {
-                        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + (size_t)m * p.OC + col;
+                        __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 7);
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
                     } else {
-                        float *o = static_cast<float *>(p.out) + (size_t)m * p.OC + col;
+                        float *o = ptx::out_at<float>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 8);
                         if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
                         else {
 #pragma unroll
@@ -645,10 +646,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         pool1::dump_prepool(v, (int)out_pix, p.M_total, row < p.m_stride, p.OC, col0, p.prepool);
                         if (p.pool_stride == 2)
                             pool1::store_chunk_s2<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
-                                                            p.m_stride, p.M_total, p.W, p.OC, col0, p.out);
+                                                            p.m_stride, p.M_total, p.W, p.OC, col0, p.out, p.out_elems);
                         else
                         pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
-                                                     p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool);
+                                                     p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool, p.out_elems);
                     } else if constexpr (POOL) {
                         if constexpr (!POOL_FIRST) {      // debug dump of the pooled-over activations (the host selects this variant for it)
                             if (p.prepool != nullptr && valid) {
@@ -692,7 +693,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                         if (valid && col < p.OC) {
                             if constexpr (OUT_BF16) {
-                                __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col;
+                                __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, out_pix * p.OC + col, 8, p.out_elems, 9);
                                 uint4 pk;
                                 __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]);
                                 __nv_bfloat162 t1 = __floats2bfloat162_rn(r8[2], r8[3]);
@@ -704,7 +705,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 pk.w = *reinterpret_cast<uint32_t *>(&t3);
                                 *reinterpret_cast<uint4 *>(o) = pk;
                             } else {
-                                float *o = static_cast<float *>(p.out) + out_pix * p.OC + col;
+                                float *o = ptx::out_at<float>(p.out, out_pix * p.OC + col, 8, p.out_elems, 10);
                                 *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
                                 *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
                             }
@@ -712,7 +713,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     } else {
                         if (valid) {
                             if constexpr (OUT_BF16) {
-                                __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + out_pix * p.OC + col0;
+                                __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, out_pix * p.OC + col0, max(0, min(32, p.OC - col0)), p.out_elems, 11);
                                 if ((p.OC & 7) == 0) {
 #pragma unroll
                                     for (int j = 0; j < 32; j += 8) {
@@ -740,7 +741,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int j = 0; j < 32; ++j)
                                     if (col0 + j < p.OC) so[j] = v[j];
                             } else {
-                                float *o = static_cast<float *>(p.out) + out_pix * p.OC + col0;
+                                float *o = ptx::out_at<float>(p.out, out_pix * p.OC + col0, max(0, min(32, p.OC - col0)), p.out_elems, 12);
                                 if ((p.OC & 3) == 0) {
 #pragma unroll
                                     for (int j = 0; j < 32; j += 4)
@@ -762,7 +763,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int row0 = p.m_base + m_tile * p.m_stride + quarter * 32;
                     const int rows = min(32, p.M_total - row0);
                     const float *src = s_out + (size_t)quarter * 32 * p.OC;
-                    float *dst = static_cast<float *>(p.out) + (size_t)row0 * p.OC;
+                    float *dst = ptx::out_at<float>(p.out, (size_t)row0 * p.OC, rows > 0 ? (size_t)rows * p.OC : 0, p.out_elems, 13);
                     const uint32_t bytes = rows > 0 ? (uint32_t)rows * p.OC * 4 : 0;
                     const bool bulk = p.tma_store && bytes > 0 && (bytes & 15) == 0 && (ptx::smem_u32(src) & 15) == 0 &&
                                       (reinterpret_cast<uintptr_t>(dst) & 15) == 0;

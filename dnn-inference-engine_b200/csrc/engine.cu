@@ -104,7 +104,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
     } else if (b.family == DNNB_KERNEL_UMMA_CONV0) {
         conv0::Params p = b.c0;
         p.in = in; p.out = conv_out; p.wpack = b.d_wpack;
-        p.scale = b.d_scale; p.shift = b.d_shift; p.prepool = prepool;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.prepool = prepool; p.out_elems = b.conv_out_elems;
         const bool u8 = net->cur_in_u8 && &b == &net->blocks.front();
         if (u8) { p.lut = net->d_lut_conv0; p.swap_rb = net->cur_swap_rb; }
         CK(launch_conv0(p, b.op_bf16, b.out_bf16, b.grid, st, u8));
@@ -113,22 +113,22 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
             if (encode_map_a(net, b, in)) return 1;
         }
         rowpair::Params p = b.rp;
-        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool; p.out_elems = b.conv_out_elems;
         CK((b.rp_linear ? b.rowpair->launch_linear : b.rowpair->launch)(b.map_a, b.map_b, p, b.lin_maps, b.grid, st));
     } else {
         if (b.map_a_base != in) {
             if (encode_map_a(net, b, in)) return 1;
         }
         umma_conv::Params p = b.up;
-        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool;
+        p.scale = b.d_scale; p.shift = b.d_shift; p.out = conv_out; p.prepool = prepool; p.out_elems = b.conv_out_elems;
         p.workspace = b.d_workspace; p.counters = b.d_counters; p.timeline = b.d_timeline;
         if (b.pair) {
             pairconv::Params q = b.pp;
-            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
+            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool; q.out_elems = b.conv_out_elems;
             if (q.num_m_tiles > 0) CK(b.pair->launch(b.map_a, b.map_b_pair, q, b.grid, st));
             if (b.pair_tail) {
                 pairconv::Params t = b.pp_tail;
-                t.scale = b.d_scale; t.shift = b.d_shift; t.out = conv_out; t.prepool = prepool;
+                t.scale = b.d_scale; t.shift = b.d_shift; t.out = conv_out; t.prepool = prepool; t.out_elems = b.conv_out_elems;
                 CK(b.pair_tail->launch(b.map_a, b.map_b_pair_tail, t, b.grid_pair_tail, st));
             }
         } else {
@@ -136,7 +136,7 @@ int run_block(dnnb_net *net, Block &b, const void *in, void *final_out_override,
         }
         if (b.umma_tail) {
             umma_conv::Params q = b.up_tail;
-            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool;
+            q.scale = b.d_scale; q.shift = b.d_shift; q.out = conv_out; q.prepool = prepool; q.out_elems = b.conv_out_elems;
             CK(b.umma_tail->launch(b.map_a, b.map_b_tail, q, b.grid_tail, st));
         }
     }

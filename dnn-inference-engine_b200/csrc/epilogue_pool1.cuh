@@ -17,6 +17,8 @@
 #include <cstdint>
 #include <cuda_bf16.h>
 
+#include "ptx.cuh"
+
 namespace pool1 {
 
 constexpr int kW = 13;                           // image width the fused form is compiled for
@@ -39,7 +41,7 @@ __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, f
 template <bool OUT_BF16>
 __device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[32], int quarter, int lane, int m0,
                                             int m_stride, int M_total, int H, int OC, int col0, void *out,
-                                            float *prepool) {
+                                            float *prepool, size_t out_elems) {
     const uint32_t mine = s_stage + (uint32_t)(quarter * 32 + lane) * (kPitch * 4);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) sts4(mine + 4 * j, v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -69,8 +71,8 @@ __device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[3
         if (i < n_rows) {
             // the debug dump wants the un-pooled value: it was overwritten above only when it had a right neighbour
             const float a = (h + 1 < H) ? fmaxf(x[i], x[i + kW]) : x[i];
-            if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[(size_t)(m + i) * OC + col] = __float2bfloat16_rn(a);
-            else static_cast<float *>(out)[(size_t)(m + i) * OC + col] = a;
+            if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, (size_t)(m + i) * OC + col, 1, out_elems, 14) = __float2bfloat16_rn(a);
+            else *ptx::out_at<float>(out, (size_t)(m + i) * OC + col, 1, out_elems, 15) = a;
         }
         if (++w == kW) { w = 0; if (++h == H) h = 0; }
     }
@@ -85,7 +87,7 @@ __device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[3
 // flattened-row / 2.
 template <bool OUT_BF16>
 __device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane, int m0, int m_stride, int M_total, int W,
-                                        int OC, int col0, int ncols, void *out) {
+                                        int OC, int col0, int ncols, void *out, size_t out_elems) {
     const int half_w = W >> 1;
     const int n_pooled = m_stride >> 2;
     const int col = col0 + lane;
@@ -98,15 +100,15 @@ __device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane,
         const uint32_t a = s_stage + (uint32_t)(r00 * kPitch + lane) * 4;
         const float v = fmaxf(fmaxf(lds(a), lds(a + kPitch * 4)), fmaxf(lds(a + W * kPitch * 4), lds(a + (W + 1) * kPitch * 4)));
         const size_t o = ((size_t)(orow0 + pr) * half_w + pc) * OC + col;
-        if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[o] = __float2bfloat16_rn(v);
-        else static_cast<float *>(out)[o] = v;
+        if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, o, 1, out_elems, 16) = __float2bfloat16_rn(v);
+        else *ptx::out_at<float>(out, o, 1, out_elems, 17) = v;
     }
 }
 
 // The stride-1 window walk on an already filled staging area (`ncols` <= 32 channels): second half of store_chunk.
 template <bool OUT_BF16>
 __device__ __forceinline__ void emit_s1(uint32_t s_stage, int quarter, int lane, int m0, int m_stride, int M_total, int H,
-                                        int OC, int col0, int ncols, void *out) {
+                                        int OC, int col0, int ncols, void *out, size_t out_elems) {
     const int r0 = quarter * 32;
     constexpr int kRows = 32 + kHalo + 1;
     float x[kRows];
@@ -128,8 +130,8 @@ __device__ __forceinline__ void emit_s1(uint32_t s_stage, int quarter, int lane,
     for (int i = 0; i < 32; ++i) {
         if (i < n_rows) {
             const float a = (h + 1 < H) ? fmaxf(x[i], x[i + kW]) : x[i];
-            if constexpr (OUT_BF16) static_cast<__nv_bfloat16 *>(out)[(size_t)(m + i) * OC + col] = __float2bfloat16_rn(a);
-            else static_cast<float *>(out)[(size_t)(m + i) * OC + col] = a;
+            if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, (size_t)(m + i) * OC + col, 1, out_elems, 14) = __float2bfloat16_rn(a);
+            else *ptx::out_at<float>(out, (size_t)(m + i) * OC + col, 1, out_elems, 15) = a;
         }
         if (++w == kW) { w = 0; if (++h == H) h = 0; }
     }
@@ -138,12 +140,12 @@ __device__ __forceinline__ void emit_s1(uint32_t s_stage, int quarter, int lane,
 // One 32-column chunk through the staging area with either pool (stride 1: store_chunk above; stride 2 here).
 template <bool OUT_BF16>
 __device__ __forceinline__ void store_chunk_s2(uint32_t s_stage, const float (&v)[32], int quarter, int lane, int m0, int m_stride,
-                                               int M_total, int W, int OC, int col0, void *out) {
+                                               int M_total, int W, int OC, int col0, void *out, size_t out_elems) {
     const uint32_t mine = s_stage + (uint32_t)(quarter * 32 + lane) * (kPitch * 4);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) sts4(mine + 4 * j, v[j], v[j + 1], v[j + 2], v[j + 3]);
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    emit_s2<OUT_BF16>(s_stage, quarter, lane, m0, m_stride, M_total, W, OC, col0, 32, out);
+    emit_s2<OUT_BF16>(s_stage, quarter, lane, m0, m_stride, M_total, W, OC, col0, 32, out, out_elems);
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 

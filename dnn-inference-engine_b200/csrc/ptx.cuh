@@ -2,6 +2,7 @@
 // mbarrier, TMA (cp.async.bulk.tensor tiled + im2col), tcgen05 (alloc / mma / commit / ld).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 
 namespace ptx {
@@ -266,6 +267,24 @@ __device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) { r
 // K-major, M = 128, N = n.  fmt: 1 = BF16, 2 = TF32.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t n, uint32_t m = 128) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Pointer to element `first` of an output tensor of `extent` elements, of which the stores that follow touch at most `n`.
+// A -DDNNB_BOUNDS build (python dnn-inference-engine_b200/build.py --force -DDNNB_BOUNDS) checks every such store
+// against the tensor's extent and traps with a message; the normal build compiles the check away.  compute-sanitizer
+// is closed on this GPU pool, so the parity suite run once under this build is what stands in for memcheck.
+template <typename T>
+__device__ __forceinline__ T *out_at(void *base, size_t first, size_t n, size_t extent, int site) {
+#ifdef DNNB_BOUNDS
+    if (n > 0 && first + n > extent) {
+        printf("DNNB_BOUNDS: site %d stores elements [%llu, %llu) of a tensor of %llu (block %d thread %d)\n", site,
+               (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)extent, (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+    }
+#else
+    (void)n; (void)extent; (void)site;
+#endif
+    return static_cast<T *>(base) + first;
 }
 
 __device__ __forceinline__ float round_tf32(float x) {
