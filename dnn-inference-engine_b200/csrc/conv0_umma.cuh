@@ -327,91 +327,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv0_kernel(const Params p) {
         //   1: activate, then pool (negative scales)          2: as 1, and dump the pooled-over activations (debug)
         auto epilogue_tiles = [&](auto MODE) {
             constexpr int mode = decltype(MODE)::value;
-        Coord tc = decode(tile_begin + group);
-        for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
-            const int ct = tc.ct, n = tc.n, jt = tc.jt;
-            const int w = ct * 128 + m;
-            const bool valid = w < p.W;
-            const int acc = t % kAccStages;
-            ptx::mbar_wait(bar_tfull + 8 * acc, (t / kAccStages) & 1);
-            ptx::tc_fence_after();
-            if (ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
+            Coord tc = decode(tile_begin + group);
+            for (int t = group; t < my_tiles; t += kEpilogueGroups, advance(tc, kEpilogueGroups)) {
+                const int ct = tc.ct, n = tc.n, jt = tc.jt;
+                const int w = ct * 128 + m;
+                const bool valid = w < p.W;
+                const int acc = t % kAccStages;
+                ptx::mbar_wait(bar_tfull + 8 * acc, (t / kAccStages) & 1);
+                ptx::tc_fence_after();
+                if (ct * 128 + quarter * 32 < p.W) {      // warp-uniform: skip quarters right of the image
 #pragma unroll 1
-                for (int rp = 0; rp < kTileRows / 2; ++rp) {      // pooling row pairs of the tile
-                    uint32_t raw[32];                             // [0,16): output row 2rp, [16,32): row 2rp+1
-                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kAccCols + 32 * rp, raw);
-                    ptx::tmem_ld_wait();
-                    const int orow = kTileRows * jt + 2 * rp;     // conv output row of raw[0..15]
-                    if constexpr (mode == 2) {                   // debug dump of the pooled-over activations (cold path)
-                        for (int c = 0; c < 16; ++c) {
-                            float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
-                            float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
-                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                            if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
-                            else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
-                            if (valid) {
-                                p.prepool[(((size_t)n * p.H + orow) * p.W + w) * 16 + c] = a;
-                                p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * 16 + c] = b;
+                    for (int rp = 0; rp < kTileRows / 2; ++rp) {      // pooling row pairs of the tile
+                        uint32_t raw[32];                             // [0,16): output row 2rp, [16,32): row 2rp+1
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kAccCols + 32 * rp, raw);
+                        ptx::tmem_ld_wait();
+                        const int orow = kTileRows * jt + 2 * rp;     // conv output row of raw[0..15]
+                        if constexpr (mode == 2) {                   // debug dump of the pooled-over activations (cold path)
+                            for (int c = 0; c < 16; ++c) {
+                                float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
+                                float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
+                                if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                                if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
+                                else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
+                                if (valid) {
+                                    p.prepool[(((size_t)n * p.H + orow) * p.W + w) * 16 + c] = a;
+                                    p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * 16 + c] = b;
+                                }
+                            }
+                        }
+                        float r8[8];
+                        if constexpr (mode == 0) {
+                            // all scales positive: pool the raw accumulators (2 rows here, 2 columns by shuffle),
+                            // then scale/shift + LeakyReLU + rounding on the 8 channels this lane stores
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float lo = fmaxf(__uint_as_float(raw[c]), __uint_as_float(raw[16 + c]));
+                                const float hi = fmaxf(__uint_as_float(raw[8 + c]), __uint_as_float(raw[24 + c]));
+                                const float keep = odd ? hi : lo;
+                                const float send = odd ? lo : hi;
+                                float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                                y = fmaf(y, sc8[c], sh8[c]);
+                                if (p.leaky) y = fmaxf(y, 0.1f * y);
+                                if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                                else if (p.round_tf32) y = ptx::round_tf32(y);
+                                r8[c] = y;
+                            }
+                        } else {
+                            float v[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
+                                float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
+                                if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                                float mx = fmaxf(a, b);                      // vertical max
+                                if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
+                                else if (p.round_tf32) mx = ptx::round_tf32(mx);
+                                v[c] = mx;                                   // rounding is monotone: max then round == round then max
+                            }
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float keep = odd ? v[8 + c] : v[c];
+                                const float send = odd ? v[c] : v[8 + c];
+                                r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));   // horizontal max: columns w, w^1
+                            }
+                        }
+                        if (valid) {
+                            const size_t pix = ((size_t)n * OH + (orow >> 1)) * OW + (w >> 1);
+                            if constexpr (OUT_BF16) {
+                                __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 1);
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                                *reinterpret_cast<uint4 *>(o) = pk;
+                            } else {
+                                float *o = ptx::out_at<float>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 2);
+                                *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+                                *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
                             }
                         }
                     }
-                    float r8[8];
-                    if constexpr (mode == 0) {
-                        // all scales positive: pool the raw accumulators (2 rows here, 2 columns by shuffle),
-                        // then scale/shift + LeakyReLU + rounding on the 8 channels this lane stores
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float lo = fmaxf(__uint_as_float(raw[c]), __uint_as_float(raw[16 + c]));
-                            const float hi = fmaxf(__uint_as_float(raw[8 + c]), __uint_as_float(raw[24 + c]));
-                            const float keep = odd ? hi : lo;
-                            const float send = odd ? lo : hi;
-                            float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                            y = fmaf(y, sc8[c], sh8[c]);
-                            if (p.leaky) y = fmaxf(y, 0.1f * y);
-                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
-                            else if (p.round_tf32) y = ptx::round_tf32(y);
-                            r8[c] = y;
-                        }
-                    } else {
-                        float v[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            float a = fmaf(__uint_as_float(raw[c]), s_scale[c], s_shift[c]);
-                            float b = fmaf(__uint_as_float(raw[16 + c]), s_scale[c], s_shift[c]);
-                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                            float mx = fmaxf(a, b);                      // vertical max
-                            if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
-                            else if (p.round_tf32) mx = ptx::round_tf32(mx);
-                            v[c] = mx;                                   // rounding is monotone: max then round == round then max
-                        }
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float keep = odd ? v[8 + c] : v[c];
-                            const float send = odd ? v[c] : v[8 + c];
-                            r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));   // horizontal max: columns w, w^1
-                        }
-                    }
-                    if (valid) {
-                        const size_t pix = ((size_t)n * OH + (orow >> 1)) * OW + (w >> 1);
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 1);
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                            *reinterpret_cast<uint4 *>(o) = pk;
-                        } else {
-                            float *o = ptx::out_at<float>(p.out, pix * 16 + (odd ? 8 : 0), 8, p.out_elems, 2);
-                            *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
-                            *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
-                        }
-                    }
                 }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar_tempty + 8 * acc);
             }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_tempty + 8 * acc);
-        }
         };
         if (p.prepool != nullptr) epilogue_tiles(std::integral_constant<int, 2>{});
         else if (p.pool_first) epilogue_tiles(std::integral_constant<int, 0>{});

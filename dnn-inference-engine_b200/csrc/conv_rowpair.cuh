@@ -241,110 +241,110 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         //   1: activate, then pool (negative scales)          2: as 1, and dump the pooled-over activations (debug)
         auto epilogue_tiles = [&](auto MODE) {
             constexpr int mode = decltype(MODE)::value;
-        Coord tc = decode(tile_begin + group);
-        for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
-            int ct = tc.ct, j = tc.j, n = tc.n;
-            int w = ct * 128 + m;
-            bool live = ct * 128 + quarter * 32 < p.W;     // warp-uniform: skip quarters right of the image
-            if constexpr (LINEAR) {
-                const int q = (tile_begin + t) * 128 + m;
-                const int rg = q / P;
-                n = rg / rows2;
-                j = rg - n * rows2;
-                w = q - rg * P - 2;                        // output column; the 4 pad positions of a row group fail 0 <= w < W
-                if (n >= p.B) w = -1;
-                live = true;
-            }
-            const int acc = t % ACC;
-            ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
-            ptx::tc_fence_after();
-            if (live) {
-#pragma unroll 1
-                for (int rp = 0; rp < TR / 2; ++rp) {                  // pooling row pairs of the tile
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + 2 * rp * OC;
-                const int orow = TR * j + 2 * rp;                      // conv output row of the pair's first row
-                const size_t pix = ((size_t)n * (p.H >> 1) + (orow >> 1)) * OW + (w >> 1);
-#pragma unroll 1
-                for (int c0 = 0; c0 < OC; c0 += 16) {
-                    uint32_t top[16], bot[16];
-                    ptx::tmem_ld_32x16(taddr + c0, top);         // first row of the pair
-                    ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // second row
-                    ptx::tmem_ld_wait();
-                    float v[16];
-                    if (mode == 2 && (unsigned)w < (unsigned)p.W) {     // debug dump of the pooled-over activations (cold path)
-                        for (int c = 0; c < 16; ++c) {
-                            const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
-                            float a = fmaf(__uint_as_float(top[c]), sc, sh);
-                            float b = fmaf(__uint_as_float(bot[c]), sc, sh);
-                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                            if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
-                            else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
-                            p.prepool[(((size_t)n * p.H + orow) * p.W + w) * OC + c0 + c] = a;
-                            p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * OC + c0 + c] = b;
-                        }
-                    }
-                    float r8[8];
-                    if constexpr (mode == 0) {
-                        // all scales positive: max over the 2x2 window of raw accumulators first
-                        const float4 sca = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0));
-                        const float4 scb = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0) + 4);
-                        const float4 sha = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0));
-                        const float4 shb = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0) + 4);
-                        const float sc8[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
-                        const float sh8[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float lo = fmaxf(__uint_as_float(top[c]), __uint_as_float(bot[c]));
-                            const float hi = fmaxf(__uint_as_float(top[8 + c]), __uint_as_float(bot[8 + c]));
-                            const float keep = odd ? hi : lo;
-                            const float send = odd ? lo : hi;
-                            float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                            y = fmaf(y, sc8[c], sh8[c]);
-                            if (p.leaky) y = fmaxf(y, 0.1f * y);
-                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
-                            else if (p.round_tf32) y = ptx::round_tf32(y);
-                            r8[c] = y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
-                            float a = fmaf(__uint_as_float(top[c]), sc, sh);
-                            float b = fmaf(__uint_as_float(bot[c]), sc, sh);
-                            if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
-                            float mx = fmaxf(a, b);                  // vertical max; rounding is monotone, so round after
-                            if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
-                            else if (p.round_tf32) mx = ptx::round_tf32(mx);
-                            v[c] = mx;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float keep = odd ? v[8 + c] : v[c];
-                            const float send = odd ? v[c] : v[8 + c];
-                            r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-                        }
-                    }
-                    if ((unsigned)w < (unsigned)p.W) {
-                        const size_t off = pix * OC + c0 + (odd ? 8 : 0);
-                        if constexpr (OUT_BF16) {
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
-                            uint4 pk;
-                            pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
-                            *reinterpret_cast<uint4 *>(ptx::out_at<__nv_bfloat16>(p.out, off, 8, p.out_elems, 5)) = pk;
-                        } else {
-                            float *o = ptx::out_at<float>(p.out, off, 8, p.out_elems, 6);
-                            *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
-                            *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
-                        }
-                    }
+            Coord tc = decode(tile_begin + group);
+            for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
+                int ct = tc.ct, j = tc.j, n = tc.n;
+                int w = ct * 128 + m;
+                bool live = ct * 128 + quarter * 32 < p.W;     // warp-uniform: skip quarters right of the image
+                if constexpr (LINEAR) {
+                    const int q = (tile_begin + t) * 128 + m;
+                    const int rg = q / P;
+                    n = rg / rows2;
+                    j = rg - n * rows2;
+                    w = q - rg * P - 2;                        // output column; the 4 pad positions of a row group fail 0 <= w < W
+                    if (n >= p.B) w = -1;
+                    live = true;
                 }
-                }   // rp
+                const int acc = t % ACC;
+                ptx::mbar_wait(bar_tfull + 8 * acc, (t / ACC) & 1);
+                ptx::tc_fence_after();
+                if (live) {
+#pragma unroll 1
+                    for (int rp = 0; rp < TR / 2; ++rp) {                  // pooling row pairs of the tile
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + 2 * rp * OC;
+                    const int orow = TR * j + 2 * rp;                      // conv output row of the pair's first row
+                    const size_t pix = ((size_t)n * (p.H >> 1) + (orow >> 1)) * OW + (w >> 1);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < OC; c0 += 16) {
+                        uint32_t top[16], bot[16];
+                        ptx::tmem_ld_32x16(taddr + c0, top);         // first row of the pair
+                        ptx::tmem_ld_32x16(taddr + OC + c0, bot);    // second row
+                        ptx::tmem_ld_wait();
+                        float v[16];
+                        if (mode == 2 && (unsigned)w < (unsigned)p.W) {     // debug dump of the pooled-over activations (cold path)
+                            for (int c = 0; c < 16; ++c) {
+                                const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
+                                float a = fmaf(__uint_as_float(top[c]), sc, sh);
+                                float b = fmaf(__uint_as_float(bot[c]), sc, sh);
+                                if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                                if constexpr (OUT_BF16) { a = __bfloat162float(__float2bfloat16_rn(a)); b = __bfloat162float(__float2bfloat16_rn(b)); }
+                                else if (p.round_tf32) { a = ptx::round_tf32(a); b = ptx::round_tf32(b); }
+                                p.prepool[(((size_t)n * p.H + orow) * p.W + w) * OC + c0 + c] = a;
+                                p.prepool[(((size_t)n * p.H + orow + 1) * p.W + w) * OC + c0 + c] = b;
+                            }
+                        }
+                        float r8[8];
+                        if constexpr (mode == 0) {
+                            // all scales positive: max over the 2x2 window of raw accumulators first
+                            const float4 sca = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0));
+                            const float4 scb = *reinterpret_cast<const float4 *>(s_scale + c0 + (odd ? 8 : 0) + 4);
+                            const float4 sha = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0));
+                            const float4 shb = *reinterpret_cast<const float4 *>(s_shift + c0 + (odd ? 8 : 0) + 4);
+                            const float sc8[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+                            const float sh8[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float lo = fmaxf(__uint_as_float(top[c]), __uint_as_float(bot[c]));
+                                const float hi = fmaxf(__uint_as_float(top[8 + c]), __uint_as_float(bot[8 + c]));
+                                const float keep = odd ? hi : lo;
+                                const float send = odd ? lo : hi;
+                                float y = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                                y = fmaf(y, sc8[c], sh8[c]);
+                                if (p.leaky) y = fmaxf(y, 0.1f * y);
+                                if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                                else if (p.round_tf32) y = ptx::round_tf32(y);
+                                r8[c] = y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const float sc = s_scale[c0 + c], sh = s_shift[c0 + c];
+                                float a = fmaf(__uint_as_float(top[c]), sc, sh);
+                                float b = fmaf(__uint_as_float(bot[c]), sc, sh);
+                                if (p.leaky) { a = fmaxf(a, 0.1f * a); b = fmaxf(b, 0.1f * b); }
+                                float mx = fmaxf(a, b);                  // vertical max; rounding is monotone, so round after
+                                if constexpr (OUT_BF16) mx = __bfloat162float(__float2bfloat16_rn(mx));
+                                else if (p.round_tf32) mx = ptx::round_tf32(mx);
+                                v[c] = mx;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float keep = odd ? v[8 + c] : v[c];
+                                const float send = odd ? v[c] : v[8 + c];
+                                r8[c] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                            }
+                        }
+                        if ((unsigned)w < (unsigned)p.W) {
+                            const size_t off = pix * OC + c0 + (odd ? 8 : 0);
+                            if constexpr (OUT_BF16) {
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(r8[0], r8[1]), t1 = __floats2bfloat162_rn(r8[2], r8[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(r8[4], r8[5]), t3 = __floats2bfloat162_rn(r8[6], r8[7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&t0); pk.y = *reinterpret_cast<uint32_t *>(&t1);
+                                pk.z = *reinterpret_cast<uint32_t *>(&t2); pk.w = *reinterpret_cast<uint32_t *>(&t3);
+                                *reinterpret_cast<uint4 *>(ptx::out_at<__nv_bfloat16>(p.out, off, 8, p.out_elems, 5)) = pk;
+                            } else {
+                                float *o = ptx::out_at<float>(p.out, off, 8, p.out_elems, 6);
+                                *reinterpret_cast<float4 *>(o) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+                                *reinterpret_cast<float4 *>(o + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
+                            }
+                        }
+                    }
+                    }   // rp
+                }
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(bar_tempty + 8 * acc);
             }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_tempty + 8 * acc);
-        }
         };
         if (p.prepool != nullptr) epilogue_tiles(std::integral_constant<int, 2>{});
         else if (p.pool_first) epilogue_tiles(std::integral_constant<int, 0>{});

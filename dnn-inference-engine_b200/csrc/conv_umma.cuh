@@ -370,73 +370,73 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int cw = BN / p.splits;                     // strip width in floats: a multiple of 4 (splits <= 16 <= BN / 8)
                     // the strip goes through in sub-strips of at most 32 columns (the width of the pool staging area)
                     for (int sub = 0; sub < cw; sub += 32) {
-                    const int sw = cw - sub < 32 ? cw - sub : 32;
-                    const int c4n = sw >> 2;                          // 16-byte units per row of the sub-strip
-                    // item = (row, 16-byte unit) of the strip, consecutive threads = consecutive units of a row: a warp's remote
-                    // load is then a few whole 128-byte runs of one peer's shared memory (one scattered 16 bytes per lane ran
-                    // at a tenth of the speed)
-                    for (int item = row; item < kBM * c4n; item += 128) {
-                        const int r = item / c4n, c4 = (item - r * c4n) * 4;
-                        const int m = p.m_base + m_tile * p.m_stride + r;
-                        if (m >= p.M_total) break;                    // rows ascend with the item index
-                        const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + sub + c4) * 4;
-                        float4 t4[16];
+                        const int sw = cw - sub < 32 ? cw - sub : 32;
+                        const int c4n = sw >> 2;                          // 16-byte units per row of the sub-strip
+                        // item = (row, 16-byte unit) of the strip, consecutive threads = consecutive units of a row: a warp's remote
+                        // load is then a few whole 128-byte runs of one peer's shared memory (one scattered 16 bytes per lane ran
+                        // at a tenth of the speed)
+                        for (int item = row; item < kBM * c4n; item += 128) {
+                            const int r = item / c4n, c4 = (item - r * c4n) * 4;
+                            const int m = p.m_base + m_tile * p.m_stride + r;
+                            if (m >= p.M_total) break;                    // rows ascend with the item index
+                            const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + sub + c4) * 4;
+                            float4 t4[16];
 #pragma unroll
-                        for (int peer = 0; peer < 16; ++peer) {       // all peers' loads in flight together, then summed in rank order
-                            if (peer < p.splits)
-                                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                             : "=f"(t4[peer].x), "=f"(t4[peer].y), "=f"(t4[peer].z), "=f"(t4[peer].w)
-                                             : "r"(ptx::mapa(src, (uint32_t)peer)));
-                        }
-                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int peer = 0; peer < 16; ++peer) {       // all peers' loads in flight together, then summed in rank order
+                                if (peer < p.splits)
+                                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=f"(t4[peer].x), "=f"(t4[peer].y), "=f"(t4[peer].z), "=f"(t4[peer].w)
+                                                 : "r"(ptx::mapa(src, (uint32_t)peer)));
+                            }
+                            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int peer = 0; peer < 16; ++peer) {
-                            if (peer < p.splits) { sum.x += t4[peer].x; sum.y += t4[peer].y; sum.z += t4[peer].z; sum.w += t4[peer].w; }
-                        }
-                        float v4[4] = {sum.x, sum.y, sum.z, sum.w};
-                        const int col = n_tile * BN + rank * cw + sub + c4;
+                            for (int peer = 0; peer < 16; ++peer) {
+                                if (peer < p.splits) { sum.x += t4[peer].x; sum.y += t4[peer].y; sum.z += t4[peer].z; sum.w += t4[peer].w; }
+                            }
+                            float v4[4] = {sum.x, sum.y, sum.z, sum.w};
+                            const int col = n_tile * BN + rank * cw + sub + c4;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
-                            if (p.leaky) y = fmaxf(y, 0.1f * y);
-                            if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
-                            else if (p.round_tf32) y = ptx::round_tf32(y);
-                            v4[e] = y;
+                            for (int e = 0; e < 4; ++e) {
+                                float y = fmaf(v4[e], s_scale[col + e], s_shift[col + e]);
+                                if (p.leaky) y = fmaxf(y, 0.1f * y);
+                                if constexpr (OUT_BF16) y = __bfloat162float(__float2bfloat16_rn(y));
+                                else if (p.round_tf32) y = ptx::round_tf32(y);
+                                v4[e] = y;
+                            }
+                            if constexpr (POOL1) {
+                                // the strip's rows all live in this CTA: stage the activated values, pool below
+                                if (p.prepool != nullptr && r < p.m_stride) {
+                                    for (int e = 0; e < 4; ++e)
+                                        if (col + e < p.OC) p.prepool[(size_t)m * p.OC + col + e] = v4[e];
+                                }
+                                pool1::sts4(ptx::smem_u32(s_out) + (uint32_t)(r * pool1::kPitch + c4) * 4, v4[0], v4[1], v4[2], v4[3]);
+                            } else if constexpr (OUT_BF16) {
+                                __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 7);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
+                            } else {
+                                float *o = ptx::out_at<float>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 8);
+                                if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                                else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (col + e < p.OC) o[e] = v4[e];
+                                }
+                            }
                         }
                         if constexpr (POOL1) {
-                            // the strip's rows all live in this CTA: stage the activated values, pool below
-                            if (p.prepool != nullptr && r < p.m_stride) {
-                                for (int e = 0; e < 4; ++e)
-                                    if (col + e < p.OC) p.prepool[(size_t)m * p.OC + col + e] = v4[e];
-                            }
-                            pool1::sts4(ptx::smem_u32(s_out) + (uint32_t)(r * pool1::kPitch + c4) * 4, v4[0], v4[1], v4[2], v4[3]);
-                        } else if constexpr (OUT_BF16) {
-                            __nv_bfloat16 *o = ptx::out_at<__nv_bfloat16>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 7);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (col + e < p.OC) o[e] = __float2bfloat16_rn(v4[e]);
-                        } else {
-                            float *o = ptx::out_at<float>(p.out, (size_t)m * p.OC + col, max(0, min(4, p.OC - col)), p.out_elems, 8);
-                            if ((p.OC & 3) == 0 && col + 3 < p.OC) *reinterpret_cast<float4 *>(o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                            else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (col + e < p.OC) o[e] = v4[e];
-                            }
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const int m0 = p.m_base + m_tile * p.m_stride;
+                            if (p.pool_stride == 2)
+                                pool1::emit_s2<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.W, p.OC,
+                                                         n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
+                            else
+                                pool1::emit_s1<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.H, p.OC,
+                                                         n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
+                            asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging area is rewritten by the next sub-strip
                         }
                     }
-                    if constexpr (POOL1) {
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        const int m0 = p.m_base + m_tile * p.m_stride;
-                        if (p.pool_stride == 2)
-                            pool1::emit_s2<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.W, p.OC,
-                                                     n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
-                        else
-                            pool1::emit_s1<OUT_BF16>(ptx::smem_u32(s_out), quarter, lane, m0, p.m_stride, p.M_total, p.H, p.OC,
-                                                     n_tile * BN + rank * cw + sub, sw, p.out, p.out_elems);
-                        asm volatile("bar.sync 1, 128;" ::: "memory");       // the staging area is rewritten by the next sub-strip
-                    }
-                    }   // sub
                     if (row == 0) stamp(p, 7);
                     ptx::cluster_sync_all();                          // #2: nobody reads this CTA's shared memory any more
                     continue;
@@ -472,20 +472,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 } else {
 #pragma unroll 1
-                for (int mi = 0; mi < MT; ++mi) {
-                    float4 *wrow = reinterpret_cast<float4 *>(p.workspace + split * slab +
-                                                              ((size_t)(m_tile * MT + mi) * kBM + row) * ldw + n_tile * BN);
+                    for (int mi = 0; mi < MT; ++mi) {
+                        float4 *wrow = reinterpret_cast<float4 *>(p.workspace + split * slab +
+                                                                  ((size_t)(m_tile * MT + mi) * kBM + row) * ldw + n_tile * BN);
 #pragma unroll 1
-                    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                        uint32_t raw[32];
-                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
-                        ptx::tmem_ld_wait();
+                        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                            uint32_t raw[32];
+                            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * BN + chunk * 32, raw);
+                            ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            __stcg(wrow + chunk * 8 + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
-                                                                      __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+                            for (int j = 0; j < 8; ++j)
+                                __stcg(wrow + chunk * 8 + j, make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                                                          __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])));
+                        }
                     }
-                }
                 }
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(bar_tempty + 8 * acc);
@@ -619,27 +619,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
                     } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
-                        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j);
-                        v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
-                        v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
-                        v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
-                        v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
-                    }
-                    if (p.leaky) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
-                    }
-                    if constexpr (!OUT_BF16) {
-                        if (p.round_tf32) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + col0 + j);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + col0 + j);
+                            v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
+                            v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
+                            v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
+                            v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
                         }
-                    } else {   // round before pooling: the reference pools the stored values
+                        if (p.leaky) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-                    }
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                        }
+                        if constexpr (!OUT_BF16) {
+                            if (p.round_tf32) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = ptx::round_tf32(v[j]);
+                            }
+                        } else {   // round before pooling: the reference pools the stored values
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                        }
                     }
 
                     if constexpr (POOL1) {
@@ -648,8 +648,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             pool1::store_chunk_s2<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
                                                             p.m_stride, p.M_total, p.W, p.OC, col0, p.out, p.out_elems);
                         else
-                        pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
-                                                     p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool, p.out_elems);
+                            pool1::store_chunk<OUT_BF16>(ptx::smem_u32(s_out), v, quarter, lane, p.m_base + (m_tile * MT + mi) * p.m_stride,
+                                                         p.m_stride, p.M_total, p.H, p.OC, col0, p.out, p.prepool, p.out_elems);
                     } else if constexpr (POOL) {
                         if constexpr (!POOL_FIRST) {      // debug dump of the pooled-over activations (the host selects this variant for it)
                             if (p.prepool != nullptr && valid) {

@@ -46,7 +46,6 @@ struct Knobs {
     bool no_pool1_fusion = false;    // DNNB_NO_POOL1_FUSION  block 5: the stride-1 SAME pool as a separate kernel
     bool no_cluster_splitk = false;  // DNNB_NO_CLUSTER_SPLITK latency plan: split-K through the global workspace, not cluster DSMEM
     bool no_tma_store = false;       // DNNB_NO_TMA_STORE     epilogues store with per-thread st.global instead of bulk copies
-    bool no_l2_prefetch = false;     // DNNB_NO_L2_PREFETCH   latency plan: no L2 prefetch of the later blocks' weights
     bool verbose_plan = false;       // DNNB_VERBOSE_PLAN     print planning decisions to stderr
 };
 
@@ -67,7 +66,7 @@ const KnobDef g_knob_defs[] = {
     {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1}, {"DNNB_PAIR_FORCE_TAIL", true, 0, 1},
     {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
     {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
-    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_NO_L2_PREFETCH", true, 0, 1}, {"DNNB_VERBOSE_PLAN", true, 0, 1},
+    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_VERBOSE_PLAN", true, 0, 1},
 };
 
 // Reads the switches.  `active` receives "NAME=value" for every switch that is set to something other than
@@ -138,7 +137,6 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.no_pool1_fusion = value("DNNB_NO_POOL1_FUSION", 0) != 0;
     k.no_cluster_splitk = value("DNNB_NO_CLUSTER_SPLITK", 0) != 0;
     k.no_tma_store = value("DNNB_NO_TMA_STORE", 0) != 0;
-    k.no_l2_prefetch = value("DNNB_NO_L2_PREFETCH", 0) != 0;
     k.verbose_plan = value("DNNB_VERBOSE_PLAN", 0) != 0;
     return bad ? 1 : 0;
 }

@@ -54,6 +54,13 @@ class StreamingDetector:
         self.seconds = 0.0
 
     # -- one job ----------------------------------------------------------------------------------
+    def _queue(self, slot, n):
+        buf = self._frames[slot].array
+        if n < self.batch:
+            buf[n:] = 0                                   # a short last job is padded with black frames
+        self.net.detect_async(buf, self._dets[slot].array, self._counts[slot].array, self.bgr)
+        self._pending.append((slot, n))
+
     def submit(self, frames):
         """Queues one job of up to `batch` frames ([n, h, w, 3] uint8; a short last job is padded).  At most two
         jobs are in flight: when both slots are busy this first collects (and returns) the older job's boxes."""
@@ -62,12 +69,8 @@ class StreamingDetector:
             raise ValueError("frames must be uint8 [1..%d, %d, %d, 3], got %s %s" % (self.batch, self.frame_hw[0], self.frame_hw[1], frames.dtype, frames.shape))
         done = self.collect() if len(self._pending) == 2 else None
         slot = self.net.next_slot()
-        buf = self._frames[slot].array
-        buf[:frames.shape[0]] = frames
-        if frames.shape[0] < self.batch:
-            buf[frames.shape[0]:] = 0
-        self.net.detect_async(buf, self._dets[slot].array, self._counts[slot].array, self.bgr)
-        self._pending.append((slot, frames.shape[0]))
+        self._frames[slot].array[:frames.shape[0]] = frames
+        self._queue(slot, frames.shape[0])
         return done
 
     def collect(self):
@@ -88,19 +91,28 @@ class StreamingDetector:
     # -- the loop ---------------------------------------------------------------------------------
     def run(self, frames):
         """frames: iterable of [h, w, 3] uint8 frames (cv2.VideoCapture.read order).  Yields every frame's label
-        boxes, in order, while later frames are already in flight."""
+        boxes, in order, while later frames are already in flight.  Each frame is copied once, straight into the
+        page-locked buffer of the pipeline slot its job will use."""
         t0 = time.perf_counter()
-        chunk = []
-        for f in frames:
-            chunk.append(f)
-            if len(chunk) == self.batch:
-                done = self.submit(np.stack(chunk))
-                chunk = []
-                for boxes in done or []:
+        it = iter(frames)
+        shape = self.frame_hw + (3,)
+        while True:
+            if len(self._pending) == 2:                   # the slot about to be filled still belongs to the oldest job
+                for boxes in self.collect():
                     yield boxes
-        if chunk:
-            for boxes in self.submit(np.stack(chunk)) or []:
-                yield boxes
+            slot = self.net.next_slot()
+            buf = self._frames[slot].array
+            n = 0
+            for f in it:
+                if f.dtype != np.uint8 or f.shape != shape:
+                    raise ValueError("frames must be uint8 %s, got %s %s" % (shape, f.dtype, f.shape))
+                buf[n] = f
+                n += 1
+                if n == self.batch:
+                    break
+            if n == 0:
+                break
+            self._queue(slot, n)
         while self._pending:
             for boxes in self.collect():
                 yield boxes
