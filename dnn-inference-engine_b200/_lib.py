@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdnn_b200.so")
+LIB_PATH = os.environ.get("LIBDNN_B200_PATH") or os.path.join(HERE, "libdnn_b200.so")     # override: A/B runs of two builds
 
 TF32, BF16, FP32 = 0, 1, 2
 PRECISIONS = {"tf32": TF32, "bf16": BF16, "fp32": FP32}
