@@ -17,8 +17,9 @@
 // starting at OC max(0, r-2).  The epilogue thread of lane m holds every row of pixel column m:
 // vertical max in registers, horizontal max by one shuffle.
 //
-// CTA = 352 threads: warp 0 TMA producer, warps 1-2 MMA issuers (alternate tiles; warp 1 owns TMEM),
-// 2 x 4 epilogue warps that alternate tiles.  One channel chunk only: IC * elem_size must equal the swizzle span (32/64/128 B).
+// CTA = 608 threads: warp 0 TMA producer, warps 1-2 MMA issuers (alternate tiles; warp 1 owns TMEM),
+// 4 x 4 epilogue warps; group g takes tiles g, g + 4, ... (block 1 was epilogue-bound with two groups: each warp
+// is a chain of dependent TMEM loads, maxima, shuffles and stores that keeps its scheduler busy 70 % of the time).  One channel chunk only: IC * elem_size must equal the swizzle span (32/64/128 B).
 #pragma once
 #include <cstdint>
 #include <type_traits>
@@ -30,7 +31,8 @@
 namespace rowpair {
 
 constexpr int kMmaWarps = 2;      // tiles alternate between two issuing warps: the MMAs are small, issue-bound
-constexpr int kThreads = (1 + kMmaWarps + 8) * 32;
+constexpr int kEpiGroups = 4;     // epilogue groups of four warps (one per TMEM lane quarter); group g takes tiles g, g + 4, ...
+constexpr int kThreads = (1 + kMmaWarps + 4 * kEpiGroups) * 32;
 constexpr int kPatchW = 130;      // 128 columns + left/right halo
 
 // LINEAR tiling (template flag): instead of 128-column tiles of the image (416, 208 and 104 columns are
@@ -83,6 +85,7 @@ struct Cfg {
     static_assert(STAGES >= 2, "need two patch stages");
     // one owner per ring slot (see conv0_umma.cuh): stages and accumulators never change their MMA warp
     static_assert(STAGES % kMmaWarps == 0 && ACC_STAGES % kMmaWarps == 0, "one owner warp per ring slot");
+    static_assert(ACC_STAGES % kEpiGroups == 0 || kEpiGroups % ACC_STAGES == 0, "one epilogue group per accumulator slot");
     static_assert(ACC_STAGES >= 2 && TMEM_COLS <= 512, "need two accumulator stages");
     static_assert(W_DJ_BYTES % 1024 == 0, "weight slabs must keep the swizzle phase");
     static_assert(OC % 16 == 0 && 3 * OC <= 256, "weights of one dj must fit one TMA box");
@@ -242,7 +245,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         auto epilogue_tiles = [&](auto MODE) {
             constexpr int mode = decltype(MODE)::value;
             Coord tc = decode(tile_begin + group);
-            for (int t = group; t < my_tiles; t += 2, advance(tc, 2)) {
+            for (int t = group; t < my_tiles; t += kEpiGroups, advance(tc, kEpiGroups)) {
                 int ct = tc.ct, j = tc.j, n = tc.n;
                 int w = ct * 128 + m;
                 bool live = ct * 128 + quarter * 32 < p.W;     // warp-uniform: skip quarters right of the image
