@@ -96,6 +96,11 @@ int dnnb_net_add_block(dnnb_net *net, const float *kernel, int kh, int kw, int i
  * programmatic dependent launch, and dnnb_net_forward_device replayed from a CUDA graph per
  * (dev_in, dev_out) pair from the second call on (the first call launches directly and sets function
  * attributes and tensor maps).  DNNB_NO_PDL / DNNB_NO_GRAPH switch the last two off.
+ * Residency: blocks whose K slices are reduced through the global workspace (the 13x13x1024 blocks at batch 1) wait
+ * for their sibling CTAs inside the kernel; the launch is cooperative, or -- under programmatic dependent launch, where
+ * that attribute is not available -- relies on its grid (<= one CTA per SM) having the device to itself: run ONE
+ * latency-plan network per device at a time (a sibling that never becomes resident ends in a bounded wait and a trap
+ * that the next call reports, not in a hang).  Blocks split over thread-block clusters carry no such assumption.
  * Streams: the *_async host calls pipeline on three streams owned by the network.  The device-entry calls run on
  * the caller's stream (or the network's own when NULL); those of them that use the network's own staging /
  * result buffers (dev_out == NULL, uint8 input that needs a preprocessing pass, dnnb_net_detect_device) order
