@@ -253,6 +253,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         n0[i] = ((m_tile / (p.tiles_w * p.tiles_h)) * MT + i) * p.nb;
                     }
                 }
+                // (tap, channel chunk) of the next K block, advanced incrementally: one elected thread issues every copy of
+                // the CTA, and two integer divisions per K block were a third of its instructions (profiles/r02_SUMMARY.md)
+                int tap = (ks_lo * KBS) / p.c_chunks, cc = ks_lo * KBS - tap * p.c_chunks;
+                int di = tap / p.KW, dj = tap - di * p.KW;
                 for (int ks = ks_lo; ks < ks_hi; ++ks) {
                     const bool armed = early > 0;        // slot armed and its B tiles in flight since before the wait
                     if (armed) --early;
@@ -263,10 +267,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const uint32_t sb = sa + KBS * MT * C::A_TILE;
 #pragma unroll
                     for (int j = 0; j < KBS; ++j) {
-                        const int kb = ks * KBS + j;
-                        const int tap = kb / p.c_chunks;
-                        const int cc = kb - tap * p.c_chunks;
-                        const int di = tap / p.KW, dj = tap - di * p.KW;
 #pragma unroll
                         for (int i = 0; i < MT; ++i) {
                             const uint32_t dst = sa + (j * MT + i) * C::A_TILE;
@@ -277,6 +277,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 ptx::tma_load_4d(dst, &map_a, full, cc * BKC, w0[i] + dj - p.PL, h0[i] + di - p.PT, n0[i]);
                         }
                         if (!armed) ptx::tma_load_4d(sb + j * C::B_TILE, &map_b, full, 0, n_tile * BN, cc, tap);
+                        if (++cc == p.c_chunks) {
+                            cc = 0;
+                            ++tap;
+                            if (++dj == p.KW) { dj = 0; ++di; }
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
