@@ -467,6 +467,14 @@ int dnnb_net_finalize(dnnb_net *net) {
                 plan_block(net, i, true);
                 if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
             }
+        } else if (net->knobs.latency) {
+            // small batches: 128-wide N tiles (twice the tiles, half the K slices per tile) unless that costs a fused pool
+            b.lat_bn = net->knobs.lat_bn > 0 ? net->knobs.lat_bn : 128;
+            plan_block(net, i, in_bf16);
+            if (b.pool_separate && net->knobs.lat_bn == 0) {
+                b.lat_bn = 0;
+                plan_block(net, i, in_bf16);
+            }
         } else {
             plan_block(net, i, in_bf16);
         }

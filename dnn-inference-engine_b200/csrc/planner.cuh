@@ -46,6 +46,7 @@ struct Knobs {
     bool no_pool1_fusion = false;    // DNNB_NO_POOL1_FUSION  block 5: the stride-1 SAME pool as a separate kernel
     bool no_cluster_splitk = false;  // DNNB_NO_CLUSTER_SPLITK latency plan: split-K through the global workspace, not cluster DSMEM
     bool no_tma_store = false;       // DNNB_NO_TMA_STORE     epilogues store with per-thread st.global instead of bulk copies
+    int lat_bn = 0;                  // DNNB_LAT_BN=n         latency plan: cap on the N tile for every block (default: 128 where it keeps the pools fused)
     bool verbose_plan = false;       // DNNB_VERBOSE_PLAN     print planning decisions to stderr
 };
 
@@ -66,7 +67,7 @@ const KnobDef g_knob_defs[] = {
     {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1}, {"DNNB_PAIR_FORCE_TAIL", true, 0, 1},
     {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
     {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
-    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_VERBOSE_PLAN", true, 0, 1},
+    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_VERBOSE_PLAN", true, 0, 1}, {"DNNB_LAT_BN", false, 0, 256},
 };
 
 // Reads the switches.  `active` receives "NAME=value" for every switch that is set to something other than
@@ -138,6 +139,7 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.no_cluster_splitk = value("DNNB_NO_CLUSTER_SPLITK", 0) != 0;
     k.no_tma_store = value("DNNB_NO_TMA_STORE", 0) != 0;
     k.verbose_plan = value("DNNB_VERBOSE_PLAN", 0) != 0;
+    k.lat_bn = value("DNNB_LAT_BN", 0);
     return bad ? 1 : 0;
 }
 
@@ -155,6 +157,7 @@ struct Block {
     // plan
     int family = DNNB_KERNEL_SIMT;
     bool pool_fused = false, pool_separate = false;
+    int lat_bn = 0;                             // latency plan: cap on the N tile (0 = none)
     bool in_bf16 = false, out_bf16 = false;     // storage types
     bool round_tf32 = false;
     const UmmaEntry *umma = nullptr;
@@ -421,7 +424,10 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
         const int row_bytes = b.ic * es;
         const int swz = row_bytes >= 128 ? 128 : row_bytes;
         const bool k_ok = (row_bytes == 32 || row_bytes == 64 || row_bytes % 128 == 0);
-        const int bn = b.oc <= 32 ? 32 : b.oc <= 64 ? 64 : b.oc <= 128 ? 128 : 256;
+        int bn = b.oc <= 32 ? 32 : b.oc <= 64 ? 64 : b.oc <= 128 ? 128 : 256;
+        // latency plan: a narrower N tile means more tiles and fewer K slices per tile -- half the partial-sum bytes per CTA
+        // in both reduction phases (dnnb_net_finalize tries 128 first and falls back when that would un-fuse a pool)
+        if (kn.latency && b.lat_bn > 0 && bn > b.lat_bn) bn = b.lat_bn;
         const int ocp = round_up(b.oc, bn);
         const int c_chunks = row_bytes / swz;
         const int total_kb = b.kh * b.kw * c_chunks;
@@ -452,25 +458,29 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 // stages per ~2 us round trip, so a K loop of up to three ring passes stays whole (measured, batch 1:
                 // block 3, 18 K blocks on 6 stages, 21.5 us split four ways, 14.8 us whole).
                 const bool long_k = total_kstages > 3 * ent->stages || kn.split_min_stages > 0;
-                if (fuse || !(tiles_mn * 2 <= net->num_sms && total_kstages >= 8 && long_k && kn.latency)) return;
+                if (fuse || !(tiles_mn * 2 <= net->num_sms && total_kstages >= 8 && kn.latency)) return;
                 int sp = net->num_sms / tiles_mn;
                 const int min_stages = kn.split_min_stages > 0 ? kn.split_min_stages : 4;
                 if (sp > total_kstages / min_stages) sp = total_kstages / min_stages;
                 if (sp < 2) return;
-                splits = sp;
                 // Cluster split-K: the K slices of a tile are the CTAs of one thread-block cluster (2, 4, 8 or 16) and the
                 // partial sums are reduced through distributed shared memory instead of a workspace in global memory
                 // guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once -- and not at the
                 // price of the weight stream's parallelism (8 tiles x clusters of 8 = 64 CTAs stream a 13x13x1024 layer
-                // twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use.
-                if (kn.no_cluster_splitk || mt_ != 1 || ent->key.stage_out || !ent->max_clusters) return;
-                int spc = 16;
-                while (spc > sp) spc /= 2;
-                if (kn.verbose_plan)
-                    for (int c = 16; c >= 2; --c)
-                        fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, ent->max_clusters(c));
-                while (spc >= 2 && ent->max_clusters(spc) < tiles_mn) spc /= 2;
-                if (spc >= 2 && 4 * spc >= 3 * sp) { splits = spc; cluster = 1; }
+                // twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use.  It costs ~3 us
+                // where the workspace form costs ~7, so it also pays for K loops too short for the latter when the tiles
+                // alone would leave most SMs idle (measured, batch 1 BF16: block 8, 2 tiles, 14.4 -> 8.1 us; block 3, 26
+                // tiles of 9 K blocks, 10.4 -> 14.9 us).
+                if (!kn.no_cluster_splitk && mt_ == 1 && !ent->key.stage_out && ent->max_clusters && (long_k || tiles_mn * 8 <= net->num_sms)) {
+                    int spc = 16;
+                    while (spc > sp) spc /= 2;
+                    if (kn.verbose_plan)
+                        for (int c = 16; c >= 2; --c)
+                            fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, ent->max_clusters(c));
+                    while (spc >= 2 && ent->max_clusters(spc) < tiles_mn) spc /= 2;
+                    if (spc >= 2 && 4 * spc >= 3 * sp) { splits = spc; cluster = 1; return; }
+                }
+                if (long_k) splits = sp;
             };
             int ipool = 0;           // 0 none, 1 = 2x2/1 SAME, 2 = 2x2/2
             int stride = umma_conv::kBM;
