@@ -89,19 +89,37 @@ template <bool OUT_BF16>
 __device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane, int m0, int m_stride, int M_total, int W,
                                         int OC, int col0, int ncols, void *out, size_t out_elems) {
     const int half_w = W >> 1;
-    const int n_pooled = m_stride >> 2;
+    const int n_pooled = m_stride >> 2;               // <= 32: at most 8 per warp
     const int col = col0 + lane;
     if (lane >= ncols || col >= OC) return;
     const int orow0 = (m0 / W) >> 1;                  // pooled flattened row of the tile's first row pair
-    for (int q = quarter; q < n_pooled; q += 4) {
+    // all windows of this warp first (up to 8 x 4 loads in flight), then the maxima and the stores: one window after
+    // the other, each behind its four dependent loads, made this the longest phase of the batch-1 kernels
+    float v[8][4];
+    size_t o[8];
+    bool live[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int q = quarter + 4 * k;
         const int pr = q / half_w, pc = q - pr * half_w;
         const int r00 = 2 * pr * W + 2 * pc;
-        if (m0 + r00 + W + 1 >= M_total) break;       // pooled pixels ascend with q: everything further lies past the batch
-        const uint32_t a = s_stage + (uint32_t)(r00 * kPitch + lane) * 4;
-        const float v = fmaxf(fmaxf(lds(a), lds(a + kPitch * 4)), fmaxf(lds(a + W * kPitch * 4), lds(a + (W + 1) * kPitch * 4)));
-        const size_t o = ((size_t)(orow0 + pr) * half_w + pc) * OC + col;
-        if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, o, 1, out_elems, 16) = __float2bfloat16_rn(v);
-        else *ptx::out_at<float>(out, o, 1, out_elems, 17) = v;
+        live[k] = q < n_pooled && m0 + r00 + W + 1 < M_total;       // windows past the batch are skipped
+        o[k] = ((size_t)(orow0 + pr) * half_w + pc) * OC + col;
+        if (live[k]) {
+            const uint32_t a = s_stage + (uint32_t)(r00 * kPitch + lane) * 4;
+            v[k][0] = lds(a);
+            v[k][1] = lds(a + kPitch * 4);
+            v[k][2] = lds(a + W * kPitch * 4);
+            v[k][3] = lds(a + (W + 1) * kPitch * 4);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (live[k]) {
+            const float r = fmaxf(fmaxf(v[k][0], v[k][1]), fmaxf(v[k][2], v[k][3]));
+            if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, o[k], 1, out_elems, 16) = __float2bfloat16_rn(r);
+            else *ptx::out_at<float>(out, o[k], 1, out_elems, 17) = r;
+        }
     }
 }
 

@@ -465,12 +465,15 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                 if (sp < 2) return;
                 // Cluster split-K: the K slices of a tile are the CTAs of one thread-block cluster (2, 4, 8 or 16) and the
                 // partial sums are reduced through distributed shared memory instead of a workspace in global memory
-                // guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once -- and not at the
-                // price of the weight stream's parallelism (8 tiles x clusters of 8 = 64 CTAs stream a 13x13x1024 layer
-                // twice as long as 144 CTAs do): at least 3/4 of the CTAs the workspace form would use.  It costs ~3 us
-                // where the workspace form costs ~7, so it also pays for K loops too short for the latter when the tiles
-                // alone would leave most SMs idle (measured, batch 1 BF16: block 8, 2 tiles, 14.4 -> 8.1 us; block 3, 26
-                // tiles of 9 K blocks, 10.4 -> 14.9 us).
+                // guarded by counters (conv_umma.cuh).  Needs every tile's cluster resident at once, which caps the slices
+                // (8 tiles: clusters of 8 at most on this part), so the two forms are compared with a small cost model from
+                // the measured phase times (tools/batch1_timeline.py, batch 1): a K block streams in ~1.7 ns per column of
+                // the N tile; the cluster reduction takes ~1.5 us + the tile's bytes over distributed shared memory at
+                // ~40 GB/s per SM, the workspace form ~7.5 (BN 128) / 9 us (BN 256) -- plus a pool kernel where one follows.
+                // The cluster form also pays for K loops too short for the workspace form when the tiles alone would leave
+                // most SMs idle (BF16: block 8, 2 tiles, 14.4 -> 8.1 us; but block 3, 26 tiles of 9 K blocks, 10.4 -> 14.9).
+                const double t_kb = 0.0017 * bn;
+                const double cost_ws = long_k ? (double)total_kstages / sp * t_kb + (bn > 128 ? 9.0 : 7.5) + (b.pool_k > 0 ? 5.0 : 0.0) : 1e9;
                 if (!kn.no_cluster_splitk && mt_ == 1 && !ent->key.stage_out && ent->max_clusters && (long_k || tiles_mn * 8 <= net->num_sms)) {
                     int spc = 16;
                     while (spc > sp) spc /= 2;
@@ -478,7 +481,11 @@ void plan_block(dnnb_net *net, size_t i, bool in_bf16) {
                         for (int c = 16; c >= 2; --c)
                             fprintf(stderr, "block %zu: tiles_mn %d, clusters of %d resident at once: %d\n", i, tiles_mn, c, ent->max_clusters(c));
                     while (spc >= 2 && ent->max_clusters(spc) < tiles_mn) spc /= 2;
-                    if (spc >= 2 && 4 * spc >= 3 * sp) { splits = spc; cluster = 1; return; }
+                    const double cost_cl = spc >= 2 ? (double)total_kstages / spc * t_kb + 1.5 + 0.0128 * bn : 1e9;
+                    if (kn.verbose_plan)
+                        fprintf(stderr, "block %zu: BN %d, %d K stages: workspace x%d ~%.1f us, cluster x%d ~%.1f us\n", i, bn, total_kstages,
+                                sp, cost_ws, spc, cost_cl);
+                    if (spc >= 2 && cost_cl + 1.0 <= cost_ws) { splits = spc; cluster = 1; return; }      // a tie goes to the form with more CTAs
                 }
                 if (long_k) splits = sp;
             };
