@@ -475,6 +475,20 @@ int dnnb_net_finalize(dnnb_net *net) {
                 b.lat_bn = 0;
                 plan_block(net, i, in_bf16);
             }
+            // a block that is not split and leaves most SMs idle (block 3 at batch 1: 26 tiles) spreads by N instead:
+            // narrower N tiles, as long as the kernel family, the fused pool and "no split" survive
+            while (net->knobs.lat_bn == 0 && b.family == DNNB_KERNEL_UMMA_IM2COL && b.up.splits == 1 && !b.pair && b.bn > 32 &&
+                   b.up.num_m_tiles * b.up.num_n_tiles * 2 <= net->num_sms) {
+                const int keep = b.lat_bn;
+                const bool fused = b.pool_fused;
+                b.lat_bn = b.bn / 2;
+                plan_block(net, i, in_bf16);
+                if (b.family != DNNB_KERNEL_UMMA_IM2COL || b.up.splits != 1 || b.pool_fused != fused || b.bn != b.lat_bn) {
+                    b.lat_bn = keep;
+                    plan_block(net, i, in_bf16);
+                    break;
+                }
+            }
         } else {
             plan_block(net, i, in_bf16);
         }

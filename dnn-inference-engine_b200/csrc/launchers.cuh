@@ -190,6 +190,10 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY_P1(false, false, 256), UMMA_ENTRY_P1(false, false, 128),
     UMMA_ENTRY_P1(true, true, 256),   UMMA_ENTRY_P1(true, true, 128),
     UMMA_ENTRY_P1(true, false, 256),  UMMA_ENTRY_P1(true, false, 128),
+    // narrow N tiles for the latency plan: a short K loop that is not split spreads over the SMs by N instead
+    UMMA_ENTRY_P1(false, false, 64),  UMMA_ENTRY_P1(false, false, 32),
+    UMMA_ENTRY_P1(true, true, 64),    UMMA_ENTRY_P1(true, true, 32),
+    UMMA_ENTRY_P1(true, false, 64),   UMMA_ENTRY_P1(true, false, 32),
 };
 
 const UmmaEntry *find_umma(const UmmaKey &k) {
