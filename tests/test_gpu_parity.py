@@ -501,6 +501,28 @@ def test_unknown_environment_switch_fails_finalize(monkeypatch):
     net.close()
 
 
+def test_phase_timeline_of_the_latency_plan():
+    """dnnb_net_debug_timeline: per-CTA %globaltimer stamps of the generic kernel (tools/batch1_timeline.py).  Every CTA
+    of an armed block stamps its phases in order, and arming does not change the result."""
+    x = make_images(1, seed=100)
+    eng = _yolo_engine(1, "tf32")
+    eng.latency = True
+    ref = eng.run(x).copy()
+    net = eng._net
+    info = net.block_info(7)
+    assert info["kernel"] == "umma_im2col" and info["splits"] > 1
+    assert net.debug_timeline(7) == info["grid"]
+    out = eng.run(x)
+    np.testing.assert_array_equal(out, ref)
+    t = net.debug_timeline(7, read=True).astype(np.int64)
+    assert t.shape == (info["grid"], 8) and (t > 0).all()
+    assert (np.diff(t, axis=1) >= 0).all()                         # entry <= prologue <= ... <= stored, per CTA
+    assert (t[:, 7] - t[:, 0]).max() < 200_000                     # a block is tens of microseconds, not milliseconds
+    with pytest.raises(RuntimeError):
+        net.debug_timeline(0)                                      # block 0 does not run the generic kernel
+    eng.close()
+
+
 def test_valid_padding_and_odd_pool_take_the_cuda_core_path(oracle_libs):
     """A block the tcgen05 kernels do not cover (VALID conv, odd sizes, 3x3/2 pool) still runs on the GPU."""
     rng = np.random.default_rng(8)
