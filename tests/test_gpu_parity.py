@@ -515,9 +515,12 @@ def test_phase_timeline_of_the_latency_plan():
     out = eng.run(x)
     np.testing.assert_array_equal(out, ref)
     t = net.debug_timeline(7, read=True).astype(np.int64)
-    assert t.shape == (info["grid"], 8) and (t > 0).all()
-    assert (np.diff(t, axis=1) >= 0).all()                         # entry <= prologue <= ... <= stored, per CTA
-    assert (t[:, 7] - t[:, 0]).max() < 200_000                     # a block is tens of microseconds, not milliseconds
+    assert t.shape == (info["grid"], 8) and (t[:, :6] > 0).all()    # slots 6-7 belong to the CTAs that reduce and store
+    assert (t[:, 7] > 0).any()
+    for row in t:
+        seen = row[row > 0]
+        assert (np.diff(seen) >= 0).all()                           # entry <= prologue <= ... <= stored, per CTA
+    assert (t.max() - t[:, 0].min()) < 200_000                      # a block is tens of microseconds, not milliseconds
     with pytest.raises(RuntimeError):
         net.debug_timeline(0)                                      # block 0 does not run the generic kernel
     eng.close()
