@@ -19,6 +19,7 @@ if not os.path.exists(LIB_PATH):
                       "(nvcc, sm_100a); this engine has no CPU fallback")
 
 lib = ctypes.CDLL(LIB_PATH)
+TIMELINE_SLOTS = 10            # DNNB_TIMELINE_SLOTS of include/dnn_b200.h
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 FP = ctypes.POINTER(c_float)
@@ -343,14 +344,14 @@ class Net:
         return ms.value, n.value
 
     def debug_timeline(self, block, read=False):
-        """Arms (read=False) or reads (read=True -> uint64 [ctas, 8] of %globaltimer ns) the per-CTA phase stamps of a block."""
+        """Arms (read=False) or reads (read=True -> uint64 [ctas, TIMELINE_SLOTS] of %globaltimer ns) the per-CTA phase
+        stamps of a block (slots: include/dnn_b200.h, dnnb_net_debug_timeline)."""
         n = c_int(0)
         if not read:
             check(lib.dnnb_net_debug_timeline(self._h, block, None, ctypes.byref(n)))
             return n.value
-        check(lib.dnnb_net_debug_timeline(self._h, block, None, ctypes.byref(n))) if False else None
         grid = self.block_info(block)["grid"]
-        out = np.zeros((grid, 8), dtype=np.uint64)
+        out = np.zeros((grid, TIMELINE_SLOTS), dtype=np.uint64)
         check(lib.dnnb_net_debug_timeline(self._h, block, out.ctypes.data, ctypes.byref(n)))
         return out[:n.value]
 

@@ -24,6 +24,7 @@
 //   warps 2-5: epilogue, one TMEM lane quarter each     2 accumulator stages (tmem_full/empty)
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -77,18 +78,21 @@ struct Params {
     // through distributed shared memory, then finishes and stores that strip.  No workspace in global memory, no
     // counters, no spinning -- and rows stay together in one CTA, which is what a fused pool needs.
     int cluster_splitk;
-    // debug: per-CTA phase stamps (%globaltimer, ns) [gridDim.x][8]: 0 entry, 1 prologue done, 2 predecessor complete
-    // (griddepcontrol.wait returned), 3 first operands landed, 4 last MMA issued, 5 accumulator complete, 6 partial tile
-    // parked / workspace written and all siblings seen, 7 result stored.  NULL in production.
+    // debug: per-CTA phase stamps (%globaltimer, ns) [gridDim.x][kTimelineSlots]: 0 entry, 1 prologue done, 2 predecessor
+    // complete (griddepcontrol.wait returned), 3 first operands landed, 4 last MMA issued, 5 accumulator complete, 6 partial
+    // tile parked / workspace written and all siblings seen, 7 result stored; split-K only: 8 own partial tile written to
+    // the workspace (workspace form), 9 siblings' partial sums read and reduced (cluster form) / landed (workspace form).
+    // NULL in production.
     unsigned long long *timeline;
     size_t out_elems;     // extent of `out` in elements (checked by -DDNNB_BOUNDS builds)
 };
 
+constexpr int kTimelineSlots = 10;
 __device__ __forceinline__ void stamp(const Params &p, int slot) {
     if (p.timeline != nullptr) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.timeline[(size_t)blockIdx.x * 8 + slot] = t;
+        p.timeline[(size_t)blockIdx.x * kTimelineSlots + slot] = t;
     }
 }
 
@@ -380,7 +384,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         // item = (row, 16-byte unit) of the strip, consecutive threads = consecutive units of a row: a warp's remote
                         // load is then a few whole 128-byte runs of one peer's shared memory (one scattered 16 bytes per lane ran
                         // at a tenth of the speed)
-                        for (int item = row; item < kBM * c4n; item += 128) {
+                        // A 2x2/2 pool never looks past the tile's own row pairs: the rows behind them are not fetched.
+                        int n_rows = kBM;
+                        if constexpr (POOL1) { if (p.pool_stride == 2) n_rows = p.m_stride; }
+                        for (int item = row; item < n_rows * c4n; item += 128) {
                             const int r = item / c4n, c4 = (item - r * c4n) * 4;
                             const int m = p.m_base + m_tile * p.m_stride + r;
                             if (m >= p.M_total) break;                    // rows ascend with the item index
@@ -430,6 +437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 }
                             }
                         }
+                        if (row == 0) stamp(p, 9);
                         if constexpr (POOL1) {
                             asm volatile("bar.sync 1, 128;" ::: "memory");
                             const int m0 = p.m_base + m_tile * p.m_stride;
@@ -475,6 +483,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    if (row == 0) stamp(p, 8);
                 } else {
 #pragma unroll 1
                     for (int mi = 0; mi < MT; ++mi) {
@@ -548,6 +557,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 depart();
                 ptx::mbar_wait(bar_red, red_phase);
                 red_phase ^= 1;
+                if (row == 0) stamp(p, 9);
                 constexpr int C4 = BN / 4;
                 const float4 *red = reinterpret_cast<const float4 *>(smem);
                 for (int u = row; u < nrows * C4; u += 128) {

@@ -1154,7 +1154,7 @@ int dnnb_net_debug_timeline(dnnb_net *net, int block, unsigned long long *host_o
     if (!b.umma || b.pair) return fail("block %d does not run the generic tcgen05 kernel", block);
     DeviceGuard g(net->device);
     CK(dnnb_sync_streams(net));
-    const size_t bytes = (size_t)b.grid * 8 * sizeof(unsigned long long);
+    const size_t bytes = (size_t)b.grid * DNNB_TIMELINE_SLOTS * sizeof(unsigned long long);
     if (!host_out) {                         // arm: allocate + clear; graphs recorded without the pointer are dropped
         if (!b.d_timeline) CK(cudaMalloc(&b.d_timeline, bytes));
         CK(cudaMemset(b.d_timeline, 0, bytes));
@@ -1262,6 +1262,7 @@ int postprocess_host(int device, const float *pred_host, const dnnb_det *cand_ho
     if (max_det < 1 || max_det > postproc::kCand) return fail("max_det must be in [1, %d]", postproc::kCand);
     DeviceGuard g(device);
     static_assert(sizeof(dnnb_det) == sizeof(postproc::Det), "dnnb_det layout");
+    static_assert(DNNB_TIMELINE_SLOTS == umma_conv::kTimelineSlots, "timeline slots");
     const size_t n_pred = (size_t)batch * postproc::kCand * postproc::kFields;
     const size_t n_cand = (size_t)batch * postproc::kCand;
     DevBuf dpred, dcand, ddump, ddets, dcounts;

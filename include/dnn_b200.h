@@ -200,10 +200,13 @@ int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
 int dnnb_net_debug_block_limit(dnnb_net *net, int blocks);
 
 /* Debug / measurement: per-CTA phase stamps (%globaltimer, ns) of a block that runs the generic tcgen05 kernel.
- * host_out == NULL arms the block (later forwards record 8 stamps per CTA: entry, prologue done, predecessor
- * complete, first operands landed, last MMA issued, accumulator complete, split-K siblings seen, result stored);
- * host_out != NULL copies [ctas][8] stamps back.  *ctas receives the block's grid size either way.  Where the
- * micro-seconds of the batch-1 chain go (tools/batch1_timeline.py). */
+ * host_out == NULL arms the block (later forwards record DNNB_TIMELINE_SLOTS stamps per CTA: 0 entry, 1 prologue done,
+ * 2 predecessor complete, 3 first operands landed, 4 last MMA issued, 5 accumulator complete, 6 split-K siblings seen,
+ * 7 result stored, and for split-K blocks 8 own partial tile written to the workspace, 9 siblings' partial sums
+ * read; a phase a CTA does not go through stays 0); host_out != NULL copies [ctas][DNNB_TIMELINE_SLOTS] stamps back.
+ * *ctas receives the block's grid size either way.  Where the micro-seconds of the batch-1 chain go
+ * (tools/batch1_timeline.py). */
+#define DNNB_TIMELINE_SLOTS 10
 int dnnb_net_debug_timeline(dnnb_net *net, int block, unsigned long long *host_out, int *ctas);
 
 int dnnb_net_destroy(dnnb_net *net);

@@ -515,9 +515,9 @@ def test_phase_timeline_of_the_latency_plan():
     out = eng.run(x)
     np.testing.assert_array_equal(out, ref)
     t = net.debug_timeline(7, read=True).astype(np.int64)
-    assert t.shape == (info["grid"], 8) and (t[:, :6] > 0).all()    # slots 6-7 belong to the CTAs that reduce and store
+    assert t.shape == (info["grid"], _lib.TIMELINE_SLOTS) and (t[:, :6] > 0).all()    # slots 6-7 belong to the CTAs that reduce and store
     assert (t[:, 7] > 0).any()
-    for row in t:
+    for row in t[:, [0, 1, 2, 3, 4, 5, 8, 6, 9, 7]]:              # in phase order; 8-9 are the split-K sub-phases
         seen = row[row > 0]
         assert (np.diff(seen) >= 0).all()                           # entry <= prologue <= ... <= stored, per CTA
     assert (t.max() - t[:, 0].min()) < 200_000                      # a block is tens of microseconds, not milliseconds

@@ -33,12 +33,14 @@ for _ in range(3):                                  # the third forward is a gra
 net.sync()
 stamps = {i: net.debug_timeline(i, read=True).astype(np.int64) for i in blocks}
 t0 = min(int(s[:, 0][s[:, 0] > 0].min()) for s in stamps.values())
-names = ["entry", "prologue", "pred done", "1st operands", "last MMA", "acc done", "siblings seen", "stored"]
+names = ["entry", "prologue", "pred done", "1st operands", "last MMA", "acc done", "siblings seen", "stored", "partial written", "partials read"]
+order = [0, 1, 2, 3, 4, 5, 8, 6, 9, 7]
 for i in blocks:
     s = stamps[i] - t0
     bi = net.block_info(i)
     print("block %d  grid %d splits %d cluster %d" % (i, bi["grid"], bi["splits"], bi["cluster_splitk"]))
-    for j, nm in enumerate(names):
+    for j in order:
+        nm = names[j]
         col = s[:, j][stamps[i][:, j] > 0]
         if col.size:
             print("   %-14s min %7.2f  median %7.2f  max %7.2f us" % (nm, col.min() / 1e3, np.median(col) / 1e3, col.max() / 1e3))
