@@ -387,8 +387,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         // A 2x2/2 pool never looks past the tile's own row pairs: the rows behind them are not fetched.
                         int n_rows = kBM;
                         if constexpr (POOL1) { if (p.pool_stride == 2) n_rows = p.m_stride; }
+                        const int c4sh = __ffs(c4n) - 1;                  // BN and the cluster size are powers of two: so is c4n
                         for (int item = row; item < n_rows * c4n; item += 128) {
-                            const int r = item / c4n, c4 = (item - r * c4n) * 4;
+                            const int r = item >> c4sh, c4 = (item & (c4n - 1)) * 4;
                             const int m = p.m_base + m_tile * p.m_stride + r;
                             if (m >= p.M_total) break;                    // rows ascend with the item index
                             const uint32_t src = smem_base + (uint32_t)r * PITCH + (uint32_t)(rank * cw + sub + c4) * 4;

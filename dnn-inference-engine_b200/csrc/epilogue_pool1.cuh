@@ -92,19 +92,23 @@ __device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane,
     const int n_pooled = m_stride >> 2;               // <= 32: at most 8 per warp
     const int col = col0 + lane;
     if (lane >= ncols || col >= OC) return;
-    const int orow0 = (m0 / W) >> 1;                  // pooled flattened row of the tile's first row pair
+    // pooled flattened row of the tile's first row pair; everything below is tile-local 32-bit arithmetic and the
+    // (row, column) of window q = quarter + 4k advances by counting -- at batch 1 one warp per scheduler runs this and
+    // eight integer divisions were most of the phase (470 instructions, 2.5 us)
+    const size_t base = (size_t)((m0 / W) >> 1) * half_w * OC + col;
     // all windows of this warp first (up to 8 x 4 loads in flight), then the maxima and the stores: one window after
     // the other, each behind its four dependent loads, made this the longest phase of the batch-1 kernels
     float v[8][4];
-    size_t o[8];
+    uint32_t o[8];
     bool live[8];
+    int pr = 0, pc = quarter;
+    while (pc >= half_w) { pc -= half_w; ++pr; }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int q = quarter + 4 * k;
-        const int pr = q / half_w, pc = q - pr * half_w;
         const int r00 = 2 * pr * W + 2 * pc;
         live[k] = q < n_pooled && m0 + r00 + W + 1 < M_total;       // windows past the batch are skipped
-        o[k] = ((size_t)(orow0 + pr) * half_w + pc) * OC + col;
+        o[k] = (uint32_t)(pr * half_w + pc) * (uint32_t)OC;
         if (live[k]) {
             const uint32_t a = s_stage + (uint32_t)(r00 * kPitch + lane) * 4;
             v[k][0] = lds(a);
@@ -112,13 +116,15 @@ __device__ __forceinline__ void emit_s2(uint32_t s_stage, int quarter, int lane,
             v[k][2] = lds(a + W * kPitch * 4);
             v[k][3] = lds(a + (W + 1) * kPitch * 4);
         }
+        pc += 4;
+        while (pc >= half_w) { pc -= half_w; ++pr; }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (live[k]) {
             const float r = fmaxf(fmaxf(v[k][0], v[k][1]), fmaxf(v[k][2], v[k][3]));
-            if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, o[k], 1, out_elems, 16) = __float2bfloat16_rn(r);
-            else *ptx::out_at<float>(out, o[k], 1, out_elems, 17) = r;
+            if constexpr (OUT_BF16) *ptx::out_at<__nv_bfloat16>(out, base + o[k], 1, out_elems, 16) = __float2bfloat16_rn(r);
+            else *ptx::out_at<float>(out, base + o[k], 1, out_elems, 17) = r;
         }
     }
 }
