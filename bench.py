@@ -41,7 +41,7 @@ import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
 # ncu --set full capture (profiles/), scaled to the bench micro-batch; None where not captured
-NCU_TRAFFIC = {"tf32": 1303000000, "bf16": 341200000}   # block 7 main launch, micro-batch 512: profiles/r02_ncu_forward_b512_{tf32,bf16}_summary.csv
+NCU_TRAFFIC = {"tf32": 1272852000, "bf16": 363675000}   # block 7, main + tail launch (the timed interval holds both), micro-batch 512: profiles/r02_ncu_forward_b512_{tf32,bf16}_summary.csv rows 9-10
 METRIC = "YOLOv2-tiny 416x416 images/sec"
 UNIT = "images/s"
 GFLOP_PER_IMAGE = [0.1495, 0.3987, 0.3987, 0.3987, 0.3987, 0.3987, 1.5949, 3.1898, 0.0433]
