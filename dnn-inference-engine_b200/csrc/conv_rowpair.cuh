@@ -85,7 +85,11 @@ struct Cfg {
     static_assert(STAGES >= 2, "need two patch stages");
     // one owner per ring slot (see conv0_umma.cuh): stages and accumulators never change their MMA warp
     static_assert(STAGES % kMmaWarps == 0 && ACC_STAGES % kMmaWarps == 0, "one owner warp per ring slot");
+    // epilogue groups that share one accumulator slot (each takes a share of the tile's pooling row pairs): a group
+    // visits every tile of its slot, so the slot's barrier never gets two phases ahead of a waiter
+    static constexpr int GROUPS_PER_ACC = kEpiGroups > ACC_STAGES ? kEpiGroups / ACC_STAGES : 1;
     static_assert(ACC_STAGES % kEpiGroups == 0 || kEpiGroups % ACC_STAGES == 0, "one epilogue group per accumulator slot");
+    static_assert((TR / 2) % GROUPS_PER_ACC == 0, "row pairs divide among the groups of a slot");
     static_assert(ACC_STAGES >= 2 && TMEM_COLS <= 512, "need two accumulator stages");
     static_assert(W_DJ_BYTES % 1024 == 0, "weight slabs must keep the swizzle phase");
     static_assert(OC % 16 == 0 && 3 * OC <= 256, "weights of one dj must fit one TMA box");
@@ -148,7 +152,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         ptx::prefetch_tensormap(&map_w);
         for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(bar_full + 8 * s, 1); ptx::mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < ACC; ++s) { ptx::mbar_init(bar_tfull + 8 * s, 1); ptx::mbar_init(bar_tempty + 8 * s, 128); }
+        for (int s = 0; s < ACC; ++s) { ptx::mbar_init(bar_tfull + 8 * s, 1); ptx::mbar_init(bar_tempty + 8 * s, 128 * C::GROUPS_PER_ACC); }
         ptx::mbar_init(bar_w, 1);
         ptx::fence_barrier_init();
     }
@@ -244,8 +248,13 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         //   1: activate, then pool (negative scales)          2: as 1, and dump the pooled-over activations (debug)
         auto epilogue_tiles = [&](auto MODE) {
             constexpr int mode = decltype(MODE)::value;
-            Coord tc = decode(tile_begin + group);
-            for (int t = group; t < my_tiles; t += kEpiGroups, advance(tc, kEpiGroups)) {
+            // group g serves accumulator slot g % SLOTS, i.e. tiles g % SLOTS, + SLOTS, ...; with fewer slots than groups
+            // GROUPS_PER_ACC groups share a tile, each taking RP_PER of its pooling row pairs
+            constexpr int SLOTS = kEpiGroups / C::GROUPS_PER_ACC;            // tiles in flight over the groups
+            constexpr int RP_PER = TR / 2 / C::GROUPS_PER_ACC;
+            const int rp_begin = (group / SLOTS) * RP_PER;
+            Coord tc = decode(tile_begin + group % SLOTS);
+            for (int t = group % SLOTS; t < my_tiles; t += SLOTS, advance(tc, SLOTS)) {
                 int ct = tc.ct, j = tc.j, n = tc.n;
                 int w = ct * 128 + m;
                 bool live = ct * 128 + quarter * 32 < p.W;     // warp-uniform: skip quarters right of the image
@@ -263,7 +272,7 @@ conv_rowpair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 ptx::tc_fence_after();
                 if (live) {
 #pragma unroll 1
-                    for (int rp = 0; rp < TR / 2; ++rp) {                  // pooling row pairs of the tile
+                    for (int rp = rp_begin; rp < rp_begin + RP_PER; ++rp) {     // this group's pooling row pairs of the tile
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + 2 * rp * OC;
                     const int orow = TR * j + 2 * rp;                      // conv output row of the pair's first row
                     const size_t pix = ((size_t)n * (p.H >> 1) + (orow >> 1)) * OW + (w >> 1);

@@ -269,7 +269,9 @@ cudaError_t launch_rowpair(const CUtensorMap &ma, const CUtensorMap &mw, const r
     {BF16, OBF, OC, SWZ, TR, &launch_rowpair<BF16, OBF, OC, SWZ, TR, false>, &launch_rowpair<BF16, OBF, OC, SWZ, TR, true>, \
      rowpair::Cfg<OC, SWZ, TR>::STAGES}
 // per shape in order of preference (measured on B200, batch 512): 4-row tiles win for 16->32 channels
-// (TF32 0.487 -> 0.468 ms, BF16 0.454 -> 0.396 ms; 8 rows leave too few patch stages), 2 rows for 32->64;
+// (TF32 0.487 -> 0.468 ms, BF16 0.454 -> 0.396 ms), 2 rows for 32->64.  Taller tiles need fewer MMAs per pixel (-17 /
+// -25 %) but leave two patch stages and two accumulator slots; measured in round 2 with the final kernels: 16->32 with
+// 8 rows TF32 0.443 -> 0.489 ms, BF16 0.295 -> 0.309; 32->64 BF16 with 4 rows 0.159 -> 0.204.  Not instantiated;
 // the planner takes the first entry whose TR divides the image height
 const RowpairEntry g_rowpair_table[] = {
     ROWPAIR_ENTRY(false, false, 32, 64, 4), ROWPAIR_ENTRY(false, false, 32, 64, 2),
