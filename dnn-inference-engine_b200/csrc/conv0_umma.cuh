@@ -64,7 +64,7 @@ constexpr int kPatchBytes = kPatchRows * kPatchRowBytes;
 constexpr int kWOperandBytes = 2 * 48 * 16;        // operand 0, taps (dj 0, dj 1) of one patch row: 2 K halves x 48 rows x 16 B
 constexpr int kW2OperandBytes = 2 * 64 * 16;       // operand 1, tap dj 2 of TWO consecutive patch rows: 2 K halves x 64 rows
 constexpr int kWBytes = kWOperandBytes + kW2OperandBytes;
-constexpr int kRawDepth = 6;                       // raw-pixel staging ring: tiles whose global loads are in flight
+constexpr int kRawDepth = 8;                       // raw-pixel staging ring: tiles whose global loads are in flight
 constexpr int kRawRowBytes = kPatchPx * 12;        // one patch row of raw 12-byte pixels (= kGroups * 48)
 constexpr int kRawBytes = (kPatchRows * kRawRowBytes + 127) / 128 * 128;
 // uint8 frames (IN_U8): a raw patch row is 160 3-byte pixels [w0-16, w0+144) = 480 bytes, so that both
