@@ -177,7 +177,16 @@ def batch1_latency(_lib, spec, precision, device, forwards=100, warmup=10):
     (DNNB_LATENCY_MODE=1: split-K over co-resident CTAs, kernels chained by programmatic dependent launch,
     the launch sequence replayed from a CUDA graph).  Each forward is timed on its own with CUDA events."""
     import torch
-    net = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device, latency=True)
+    # the plan the planner models, and the plan measured on this box (latency="tune" of the host API): the headline
+    # below is the measured plan when it is faster, with the modelled one beside it
+    modelled = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device, latency=True)
+    modelled_us = modelled.time_forward(10, forwards)
+    modelled.close()
+    t_tune = time.perf_counter()
+    tuned = _lib.tune_latency_widths((1, 416, 416, 3), spec, precision, device)
+    t_tune = time.perf_counter() - t_tune
+    widths = tuned["widths"] if tuned["tuned_us"] < tuned["modelled_us"] else [0] * len(spec)
+    net = _lib.Net((1, 416, 416, 3), spec, precision=precision, device=device, latency=True, latency_widths=widths)
     dev = torch.device("cuda", device)
     stream = torch.cuda.current_stream(dev)
     x = torch.rand((1, 416, 416, 3), device=dev)
@@ -212,8 +221,11 @@ def batch1_latency(_lib, spec, precision, device, forwards=100, warmup=10):
     net.close()
     return {"median_us": round(statistics.median(ts), 1), "min_us": round(min(ts), 1), "forwards": forwards,
             "launches_per_forward": launches, "precision": precision,
+            "widths_source": "measured on this box (latency='tune')" if any(widths) else "modelled (the measurement found nothing faster)",
+            "latency_widths": widths, "modelled_plan_median_us": round(modelled_us, 1), "tuning_seconds": round(t_tune, 1),
             "e2e_host_median_us": host,   # pinned host image in -> head tensor back in host memory
-            "plan": "DNNB_LATENCY_MODE=1: split-K, programmatic dependent launch chain, CUDA graph replay; input resident in HBM"}
+            "plan": "latency plan: split-K, programmatic dependent launch chain, CUDA graph replay; N-tile widths of the blocks "
+                    "measured on this box (latency='tune', dnnb_net_set_latency_widths); input resident in HBM"}
 
 
 def dist_env():

@@ -48,6 +48,7 @@ _sig("dnnb_net_add_block", c_void_p, FP, c_int, c_int, c_int, c_int, c_int, FP, 
      c_int, c_int, c_int, c_int)
 _sig("dnnb_net_finalize", c_void_p)
 _sig("dnnb_net_set_latency", c_void_p, c_int)
+_sig("dnnb_net_set_latency_widths", c_void_p, IP, c_int)
 _sig("dnnb_net_knobs", c_void_p, ctypes.c_char_p, c_int)
 _sig("dnnb_net_num_blocks", c_void_p, IP)
 _sig("dnnb_net_out_shape", c_void_p, IP, IP, IP, IP)
@@ -66,6 +67,7 @@ _sig("dnnb_net_time_blocks", c_void_p, c_int, c_int, FP)
 _sig("dnnb_net_launches_per_forward", c_void_p, IP)
 _sig("dnnb_net_debug_block_limit", c_void_p, c_int)
 _sig("dnnb_net_debug_timeline", c_void_p, c_int, c_void_p, IP)
+_sig("dnnb_net_time_forward", c_void_p, c_int, c_int, ctypes.POINTER(c_float))
 _sig("dnnb_net_profile_block", c_void_p, c_int)
 _sig("dnnb_net_profile_read", c_void_p, FP, IP)
 _sig("dnnb_net_destroy", c_void_p)
@@ -86,11 +88,11 @@ _sig("dnnb_measure_mma_peak_sustained", c_int, c_int, c_float, FP)
 
 EXPORTS = ["dnnb_last_error", "dnnb_version", "dnnb_device_count", "conv2d_mul", "bias_add", "batch_norm",
            "max_pool2d", "leaky_relu", "dnnb_net_create", "dnnb_net_add_block", "dnnb_net_finalize",
-           "dnnb_net_set_latency", "dnnb_net_knobs",
+           "dnnb_net_set_latency", "dnnb_net_set_latency_widths", "dnnb_net_knobs",
            "dnnb_net_num_blocks", "dnnb_net_out_shape", "dnnb_net_forward", "dnnb_net_forward_async",
            "dnnb_net_forward_device", "dnnb_net_forward_u8_async", "dnnb_net_forward_u8_device", "dnnb_net_sync",
            "dnnb_net_next_slot", "dnnb_net_wait_slot", "dnnb_net_block_output", "dnnb_net_block_info", "dnnb_net_debug_prepool",
-           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit", "dnnb_net_debug_timeline",
+           "dnnb_net_time_blocks", "dnnb_net_launches_per_forward", "dnnb_net_debug_block_limit", "dnnb_net_debug_timeline", "dnnb_net_time_forward",
            "dnnb_net_profile_block", "dnnb_net_profile_read", "dnnb_net_destroy", "dnnb_host_alloc",
            "dnnb_host_free", "dnnb_measure_mma_peak", "dnnb_measure_mma_peak_sustained",
            "dnnb_postprocess", "dnnb_postprocess_candidates", "dnnb_nms", "dnnb_net_set_detect",
@@ -165,10 +167,11 @@ class Net:
     """Resident fused network (dnnb_net_*).  blocks: list of dicts with keys kernel, padding,
     biases, mean, variance, gamma, epsilon, leaky, pool (None or (k, s, padding))."""
 
-    def __init__(self, in_shape, blocks, precision="tf32", device=0, latency=None):
+    def __init__(self, in_shape, blocks, precision="tf32", device=0, latency=None, latency_widths=None):
         """latency: True / False selects the small-batch latency plan for this network (split-K, PDL chain,
         CUDA-graph replay; include/dnn_b200.h, dnnb_net_finalize) regardless of DNNB_LATENCY_MODE; None leaves
-        the choice to the environment."""
+        the choice to the environment.  latency_widths: per-block N-tile widths under that plan (0 = the planner's
+        modelled choice; dnnb_net_set_latency_widths, tools/tune_latency.py)."""
         b, h, w, c = (int(v) for v in in_shape)
         self.in_shape = (b, h, w, c)
         self.precision = precision
@@ -190,6 +193,9 @@ class Net:
                                              1 if blk.get("leaky") else 0, pk, ps, pp))
             if latency is not None:
                 check(lib.dnnb_net_set_latency(self._h, 1 if latency else 0))
+            if latency_widths:
+                arr = (c_int * len(latency_widths))(*[int(v) for v in latency_widths])
+                check(lib.dnnb_net_set_latency_widths(self._h, arr, len(latency_widths)))
             check(lib.dnnb_net_finalize(self._h))
             o = [c_int(0) for _ in range(4)]
             check(lib.dnnb_net_out_shape(self._h, *[ctypes.byref(v) for v in o]))
@@ -355,6 +361,12 @@ class Net:
         check(lib.dnnb_net_debug_timeline(self._h, block, out.ctypes.data, ctypes.byref(n)))
         return out[:n.value]
 
+    def time_forward(self, warmup=10, iters=60):
+        """Median device time (us) of a forward from the network's own buffers (graph replays under the latency plan)."""
+        us = c_float(0)
+        check(lib.dnnb_net_time_forward(self._h, warmup, iters, ctypes.byref(us)))
+        return us.value
+
     def debug_block_limit(self, blocks):
         check(lib.dnnb_net_debug_block_limit(self._h, blocks))
 
@@ -420,3 +432,45 @@ def measure_mma_peak(precision="tf32", device=0, seconds=0.0):
     else:
         check(lib.dnnb_measure_mma_peak(device, PRECISIONS[precision], ctypes.byref(t)))
     return t.value
+
+
+def tune_latency_widths(in_shape, blocks, precision="tf32", device=0, iters=60, sweeps=2, margin_us=0.5, log=None):
+    """Measures the N-tile width of every generic-kernel block of a latency-plan network on this device: coordinate
+    descent over the blocks, every candidate a freshly planned network timed over whole forwards (PDL chain + graph
+    replay), because a block's best width depends on its neighbours (a grid that fills every SM keeps its successor's
+    prologue from starting early) and on the part.  Returns {"widths", "tuned_us", "modelled_us"}; pass widths as
+    Net(latency_widths=...) / dnnb_net_set_latency_widths to pin the plan (results of different plans differ by fp32
+    summation order where the number of K slices differs)."""
+    def measure(widths):
+        net = Net(in_shape, blocks, precision=precision, device=device, latency=True, latency_widths=widths)
+        try:
+            info = [net.block_info(i) for i in range(net.num_blocks)]
+            return net.time_forward(10, iters), info
+        finally:
+            net.close()
+
+    n = len(blocks)
+    widths = [0] * n
+    base, info0 = measure(widths)
+    best = base
+    tunable = [i for i in range(n) if info0[i]["kernel"] in ("umma_im2col", "umma_tiled_pool")]
+    for sweep in range(sweeps):
+        changed = False
+        for i in tunable:
+            for cand in (256, 128, 64, 32):
+                if cand == (widths[i] or info0[i]["bn_tile"]):
+                    continue
+                trial = list(widths)
+                trial[i] = cand
+                t, info = measure(trial)
+                if info[i]["bn_tile"] != cand or info[i]["kernel"] == "simt":
+                    continue                            # no kernel of that width: the planner fell back
+                if t < best - margin_us:
+                    t2, _ = measure(trial)              # a second look before a plan is kept
+                    if max(t, t2) < best - margin_us:
+                        best, widths, changed = max(t, t2), trial, True
+                if log:
+                    log("sweep %d block %d width %d: %.1f us (best %.1f)" % (sweep, i, cand, t, best))
+        if not changed:
+            break
+    return {"widths": widths, "tuned_us": best, "modelled_us": base}

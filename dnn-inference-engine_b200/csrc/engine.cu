@@ -8,6 +8,7 @@
 // ops_simt.cuh and postproc.cuh.
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -468,26 +469,42 @@ int dnnb_net_finalize(dnnb_net *net) {
                 if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
             }
         } else if (net->knobs.latency) {
-            // small batches: 128-wide N tiles (twice the tiles, half the K slices per tile) unless that costs a fused pool
-            b.lat_bn = net->knobs.lat_bn > 0 ? net->knobs.lat_bn : 128;
-            plan_block(net, i, in_bf16);
-            if (b.pool_separate && net->knobs.lat_bn == 0) {
-                b.lat_bn = 0;
+            // Small batches: the N-tile width decides how a block is cut (tiles x K slices) and through what the slices
+            // exchange their partial sums.  Every width the kernels exist for is planned and the modelled time of the
+            // plan compared (latency_cost); DNNB_LAT_BN=n forces a cap instead.
+            const int forced_bn = i < net->lat_widths.size() && net->lat_widths[i] > 0 ? net->lat_widths[i] : net->knobs.lat_bn;
+            if (forced_bn > 0) {
+                b.lat_bn = forced_bn;
                 plan_block(net, i, in_bf16);
-            }
-            // a block that is not split and leaves most SMs idle (block 3 at batch 1: 26 tiles) spreads by N instead:
-            // narrower N tiles, as long as the kernel family, the fused pool and "no split" survive
-            while (net->knobs.lat_bn == 0 && b.family == DNNB_KERNEL_UMMA_IM2COL && b.up.splits == 1 && !b.pair && b.bn > 32 &&
-                   b.up.num_m_tiles * b.up.num_n_tiles * 2 <= net->num_sms) {
-                const int keep = b.lat_bn;
-                const bool fused = b.pool_fused;
-                b.lat_bn = b.bn / 2;
-                plan_block(net, i, in_bf16);
-                if (b.family != DNNB_KERNEL_UMMA_IM2COL || b.up.splits != 1 || b.pool_fused != fused || b.bn != b.lat_bn) {
-                    b.lat_bn = keep;
+                if (b.family == DNNB_KERNEL_SIMT) {          // no tcgen05 kernel of that width: the planner's own width
+                    b.lat_bn = 0;
                     plan_block(net, i, in_bf16);
-                    break;
                 }
+            } else {
+                int best_bn = 0;
+                double best = 0.0;
+                const int cands[4] = {0, 128, 64, 32};       // 0: the planner's own width (up to 256)
+                for (int c = 0; c < 4; ++c) {
+                    b.lat_bn = cands[c];
+                    plan_block(net, i, in_bf16);
+                    if (c == 0) {
+                        best = latency_cost(b, net->num_sms);
+                        if (best < 0.0) break;               // not a block of the generic kernel: nothing to choose
+                        continue;
+                    }
+                    if (b.bn != cands[c]) continue;          // the cap did not bind: same plan as a wider candidate
+                    const double cost = latency_cost(b, net->num_sms);
+                    if (cost < 0.0) continue;
+                    if (cost + 0.2 <= best) {                // a tie goes to the wider tile
+                        best = cost;
+                        best_bn = cands[c];
+                    }
+                }
+                b.lat_bn = best_bn;
+                plan_block(net, i, in_bf16);
+                if (net->knobs.verbose_plan)
+                    fprintf(stderr, "dnnb plan: block %zu latency width %d (bn %d, splits %d, cluster %d) modelled %.1f us\n", i, best_bn,
+                            b.bn, b.up.splits, b.up.cluster_splitk, best);
             }
         } else {
             plan_block(net, i, in_bf16);
@@ -1097,6 +1114,31 @@ int dnnb_net_time_blocks(dnnb_net *net, int warmup, int iters, float *ms) {
     return 0;
 }
 
+int dnnb_net_time_forward(dnnb_net *net, int warmup, int iters, float *median_us) {
+    if (check_net(net, true)) return 1;
+    if (!median_us || iters <= 0 || warmup < 0) return fail("bad argument");
+    DeviceGuard g(net->device);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    std::vector<float> us;
+    us.reserve(iters);
+    for (int it = 0; it < warmup + iters; ++it) {
+        CK(cudaEventRecord(e0, net->stream));
+        if (dnnb_net_forward_device(net, net->d_in, nullptr, nullptr)) return 1;      // graph replay under the latency plan
+        CK(cudaEventRecord(e1, net->stream));
+        CK(cudaEventSynchronize(e1));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        if (it >= warmup) us.push_back(t * 1e3f);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    std::sort(us.begin(), us.end());
+    *median_us = us[us.size() / 2];
+    return 0;
+}
+
 int dnnb_net_profile_block(dnnb_net *net, int block) {
     if (check_net(net, true)) return 1;
     if (block >= (int)net->blocks.size()) return fail("bad block index");
@@ -1135,12 +1177,30 @@ int dnnb_net_set_latency(dnnb_net *net, int mode) {
     return 0;
 }
 
+int dnnb_net_set_latency_widths(dnnb_net *net, const int *widths, int n) {
+    if (check_net(net, false)) return 1;
+    if (net->finalized) return fail("dnnb_net_set_latency_widths must be called before dnnb_net_finalize");
+    if (n < 0 || (n > 0 && !widths)) return fail("bad argument");
+    for (int i = 0; i < n; ++i)
+        if (widths[i] != 0 && widths[i] != 32 && widths[i] != 64 && widths[i] != 128 && widths[i] != 256)
+            return fail("width %d of block %d: 0 (modelled choice), 32, 64, 128 or 256", widths[i], i);
+    net->lat_widths.assign(widths, widths + n);
+    return 0;
+}
+
 int dnnb_net_knobs(dnnb_net *net, char *buf, int buf_len) {
     if (check_net(net, true) || !buf || buf_len < 1) return fail("bad argument");
     std::string text = net->knobs_active;
     if (net->latency_override >= 0) {
         if (!text.empty()) text += ",";
         text += std::string("set_latency=") + (net->latency_override ? "1" : "0");
+    }
+    bool any_width = false;
+    for (int w : net->lat_widths) any_width = any_width || w != 0;
+    if (any_width) {
+        if (!text.empty()) text += ",";
+        text += "set_latency_widths=";
+        for (size_t i = 0; i < net->lat_widths.size(); ++i) text += (i ? "/" : "") + std::to_string(net->lat_widths[i]);
     }
     if ((int)text.size() + 1 > buf_len) return fail("buffer too small: %zu bytes needed", text.size() + 1);
     memcpy(buf, text.c_str(), text.size() + 1);

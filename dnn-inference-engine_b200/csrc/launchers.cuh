@@ -155,6 +155,7 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(false, false, 256, 128, 1, true, false),
     UMMA_ENTRY(false, false, 128, 128, 1, true, false),
     UMMA_ENTRY(false, false, 64, 128, 1, true, false),
+    UMMA_ENTRY(false, false, 32, 128, 1, true, false),
     UMMA_ENTRY(false, false, 32, 64, 3, true, false),
     // BF16 operands, bf16 storage out
     UMMA_ENTRY(true, true, 32, 32, 3, false, true),
@@ -163,6 +164,8 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(true, true, 256, 128, 1, false, true),
     UMMA_ENTRY(true, true, 256, 128, 1, true, false),
     UMMA_ENTRY(true, true, 128, 128, 1, true, false),
+    UMMA_ENTRY(true, true, 64, 128, 1, true, false),
+    UMMA_ENTRY(true, true, 32, 128, 1, true, false),
     UMMA_ENTRY(true, true, 64, 64, 3, true, false),
     UMMA_ENTRY(true, true, 32, 32, 3, true, false),
     // BF16 operands, fp32 out (a network's last block)
@@ -172,6 +175,8 @@ const UmmaEntry g_umma_table[] = {
     UMMA_ENTRY(true, false, 256, 128, 1, false, true),
     UMMA_ENTRY(true, false, 256, 128, 1, true, false),
     UMMA_ENTRY(true, false, 128, 128, 1, true, false),
+    UMMA_ENTRY(true, false, 64, 128, 1, true, false),
+    UMMA_ENTRY(true, false, 32, 128, 1, true, false),
     UMMA_ENTRY(true, false, 64, 64, 3, true, false),
     UMMA_ENTRY(true, false, 32, 32, 3, true, false),
     // 256 x 256 CTA tiles (two M tiles share each weight tile) for the long-K 13x13 layers

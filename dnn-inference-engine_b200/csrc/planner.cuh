@@ -244,6 +244,7 @@ struct dnnb_net {
     Knobs knobs;
     std::string knobs_active;            // "NAME=value,..." of the DNNB_* switches that are not at their default
     int latency_override = -1;           // dnnb_net_set_latency: -1 = DNNB_LATENCY_MODE decides
+    std::vector<int> lat_widths;         // dnnb_net_set_latency_widths: per-block N-tile width under the latency plan (0 = modelled choice)
     bool pdl = false, use_graph = false;
     struct GraphSlot {
         const void *in = nullptr;
@@ -349,6 +350,40 @@ bool all_scales_positive(const Block &b) {
     for (float v : b.scale)
         if (!(v > 0.f)) return false;
     return true;
+}
+
+// Modelled time (us) of a planned generic-kernel block at small batch, for comparing N-tile widths under the latency
+// plan (dnnb_net_finalize).  < 0: the block does not run the generic kernel (nothing to choose).  Fitted to the phase
+// stamps of tools/batch1_timeline.py and the per-block times of tools/batch1_blocks.py at batch 1 (profiles/
+// r02_SUMMARY.md); it only has to order the candidates of one block:
+//  * K loop: a CTA takes 0.10 us + 1 us per 262 KB for every K block it streams (block 3: 18 blocks of 20 KB in 2.9 us;
+//    block 7: 32 blocks of 32 KB in 7.1 us), and all CTAs together get 21 TB/s out of L2;
+//  * partial sums through the global workspace: 5.7 us + 18 ns per column of the tile (store, flag, reload, sum);
+//    through distributed shared memory: 2 us + 20 ns per column + a term that grows with the cluster (1.5 us at 8 CTAs:
+//    such a kernel's CTAs start only once whole groups of SMs are free, its prologue no longer hides behind the
+//    preceding kernel; 4 us at 16);
+//  * unsplit: 11 ns per column of epilogue; a pool that is not fused: 6 us for its own kernel.
+double latency_cost(const Block &b, int num_sms) {
+    if ((b.family != DNNB_KERNEL_UMMA_TILED && b.family != DNNB_KERNEL_UMMA_IM2COL) || !b.umma || b.pair) return -1.0;
+    const umma_conv::Params &p = b.up;
+    const int es = b.in_bf16 ? 2 : 4;
+    const int row_bytes = b.ic * es;
+    const int swz = row_bytes >= 128 ? 128 : row_bytes;
+    const int kblocks = b.kh * b.kw * (row_bytes / swz);                 // K blocks of one swizzle span
+    const int splits = p.splits > 1 ? p.splits : 1;
+    const int kb_cta = (kblocks + splits - 1) / splits;
+    const double kb_bytes = (double)(b.umma->key.mt * umma_conv::kBM + b.bn) * swz / 1024.0;     // KB per K block
+    const int ctas = p.num_m_tiles * p.num_n_tiles * splits;
+    const int waves = (ctas + num_sms - 1) / num_sms;
+    double k_time = kb_cta * (0.10 + kb_bytes / 262.0);
+    const double shared = (double)(ctas < num_sms ? ctas : num_sms) * kb_cta * kb_bytes / 21000.0;
+    if (shared > k_time) k_time = shared;
+    k_time *= waves;
+    double exchange;
+    if (splits == 1) exchange = 0.011 * b.bn;
+    else if (p.cluster_splitk) exchange = 2.0 + 0.02 * b.bn + (splits >= 16 ? 4.0 : splits >= 8 ? 1.5 : splits >= 4 ? 0.5 : 0.3);
+    else exchange = 5.7 + 0.018 * b.bn;
+    return k_time + exchange + (b.pool_separate ? 6.0 : 0.0);
 }
 
 // Decide how block `i` runs.  in_bf16: storage type of its input.

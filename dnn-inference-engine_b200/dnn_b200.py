@@ -34,7 +34,7 @@ F32_MIN = np.finfo(np.float32).min
 
 
 class DnnInferenceEngine(object):
-    def __init__(self, graph, debug=False, precision="tf32", device=0, latency=None, devices=None):
+    def __init__(self, graph, debug=False, precision="tf32", device=0, latency=None, devices=None, latency_widths=None):
         """devices=[0, 1, ...]: batch-sharded over several GPUs (sharded.MultiGpuEngine: contiguous slices of the
         batch, weights replicated once per device, no collective; the result is assembled in one host array)."""
         self.g = graph
@@ -43,6 +43,7 @@ class DnnInferenceEngine(object):
         self.device = device if devices is None else list(devices)[0]
         self.devices = None if devices is None else list(devices)
         self.latency = latency       # True: plan for single-image latency (see _lib.Net); None: DNNB_LATENCY_MODE decides
+        self.latency_widths = latency_widths   # per-block N-tile widths of that plan; latency='tune' measures them (see _build_net)
         self.save_dir = os.path.join(os.getcwd(), "intermediate")
         self._net = None
         self._net_key = None
@@ -109,8 +110,15 @@ class DnnInferenceEngine(object):
         in_shape = list(self.g.in_node.in_shape)
         if batch is not None:
             in_shape[0] = batch
-        return _lib.Net(in_shape, spec, precision=self.precision, device=self.device if device is None else device,
-                        latency=self.latency)
+        dev = self.device if device is None else device
+        if self.latency == "tune":
+            # measured plan: the N-tile widths of the latency plan are timed on this device once (a few seconds) and
+            # kept in self.latency_widths; pass them back as latency_widths= to pin the plan without measuring again
+            if self.latency_widths is None:
+                self.latency_widths = _lib.tune_latency_widths(in_shape, spec, self.precision, dev)["widths"]
+            return _lib.Net(in_shape, spec, precision=self.precision, device=dev, latency=True, latency_widths=self.latency_widths)
+        return _lib.Net(in_shape, spec, precision=self.precision, device=dev, latency=self.latency,
+                        latency_widths=self.latency_widths)
 
     def _build_sharded(self, blocks):
         import sharded

@@ -111,6 +111,14 @@ int dnnb_net_finalize(dnnb_net *net);
  * -1 = DNNB_LATENCY_MODE decides (the default).  Call before dnnb_net_finalize. */
 int dnnb_net_set_latency(dnnb_net *net, int mode);
 
+/* Latency plan only: the N-tile width (32, 64, 128, 256; 0 = the planner's modelled choice, the default) of the first
+ * n blocks.  The width decides how a block is cut into output tiles and K slices and how the slices exchange their
+ * partial sums; the planner compares modelled times (planner.cuh, latency_cost), tools/tune_latency.py measures the
+ * alternatives on the device.  A width the kernels do not exist for falls back to the planner's own.  Results of
+ * different widths differ by fp32 summation order where the number of K slices differs.  Call before
+ * dnnb_net_finalize; dnnb_net_knobs reports a non-default choice as set_latency_widths=a/b/... */
+int dnnb_net_set_latency_widths(dnnb_net *net, const int *widths, int n);
+
 /* Environment switches.  dnnb_net_finalize reads the DNNB_* variables (DESIGN.md section 4c lists them; apart
  * from DNNB_LATENCY_MODE they force a particular kernel for tests and ablation measurements) and FAILS on a
  * DNNB_* name it does not know or a value it cannot parse, so that a stale variable in a shell cannot silently
@@ -198,6 +206,12 @@ int dnnb_net_launches_per_forward(dnnb_net *net, int *n);
  * forwards at increasing limits gives each block's in-situ share of the batch-1 latency, overlap
  * between programmatically chained kernels included (tools/batch1_probe.py). */
 int dnnb_net_debug_block_limit(dnnb_net *net, int blocks);
+
+/* Measurement: median device time (us, CUDA events on the network's own stream, one forward per event pair) of
+ * `iters` forwards from the network's own input buffer (whatever it holds) into its own output, after `warmup`
+ * untimed ones.  Under the latency plan these are the graph replays a caller gets.  What tune_latency_widths of the
+ * Python binding compares candidate plans with. */
+int dnnb_net_time_forward(dnnb_net *net, int warmup, int iters, float *median_us);
 
 /* Debug / measurement: per-CTA phase stamps (%globaltimer, ns) of a block that runs the generic tcgen05 kernel.
  * host_out == NULL arms the block (later forwards record DNNB_TIMELINE_SLOTS stamps per CTA: 0 entry, 1 prologue done,

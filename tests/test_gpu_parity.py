@@ -501,6 +501,34 @@ def test_unknown_environment_switch_fails_finalize(monkeypatch):
     net.close()
 
 
+def test_latency_widths_pin_the_plan_and_tuning_measures_it():
+    """dnnb_net_set_latency_widths / latency='tune': a width per block decides tiles x K slices; whatever the choice the
+    result stays within the reordering noise of the default plan, and the measured plan is never slower than it."""
+    x = make_images(1, seed=100)
+    spec = [_layer_spec(i, w) for i, w in enumerate(make_weights(0))]
+    ref_net = _lib.Net(x.shape, spec, precision="tf32", latency=True)
+    ref = ref_net.forward(x)
+    base_bn = [ref_net.block_info(i)["bn_tile"] for i in range(9)]
+    ref_net.close()
+    widths = [0, 0, 0, 128, 128, 128, 256, 256, 128]
+    net = _lib.Net(x.shape, spec, precision="tf32", latency=True, latency_widths=widths)
+    got = net.forward(x)
+    assert [net.block_info(i)["bn_tile"] for i in range(3, 9)] == [128, 128, 128, 256, 256, 128] != base_bn[3:]
+    assert net.knobs().get("set_latency_widths") == "0/0/0/128/128/128/256/256/128"
+    assert normalised_error(got, ref) < 2e-3
+    net.close()
+    with pytest.raises(RuntimeError):
+        _lib.Net(x.shape, spec, precision="tf32", latency=True, latency_widths=[0, 0, 0, 48])
+    tuned = _lib.tune_latency_widths(x.shape, spec, "tf32", iters=20, sweeps=1)
+    assert len(tuned["widths"]) == 9 and tuned["tuned_us"] <= tuned["modelled_us"] and tuned["modelled_us"] < 200
+    g = dnn_b200.DnnGraphBuilder()
+    build_yolov2tiny(g, [1, 416, 416, 3], make_weights(0))
+    eng = dnn_b200.DnnInferenceEngine(g, False, precision="tf32", latency="tune")
+    out = eng.run(x)
+    assert eng.latency_widths is not None and normalised_error(out, ref) < 2e-3
+    eng.close()
+
+
 def test_phase_timeline_of_the_latency_plan():
     """dnnb_net_debug_timeline: per-CTA %globaltimer stamps of the generic kernel (tools/batch1_timeline.py).  Every CTA
     of an armed block stamps its phases in order, and arming does not change the result."""
