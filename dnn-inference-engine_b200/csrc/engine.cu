@@ -448,6 +448,58 @@ int dnnb_net_finalize(dnnb_net *net) {
     }
     net->pdl = net->knobs.latency && !net->knobs.no_pdl;
     net->use_graph = net->knobs.latency && !net->knobs.no_graph;
+    // ---- geometry and plan of every block (no device memory yet)
+    // Latency plan: the N-tile width decides how a block is cut (tiles x K slices) and through what the slices exchange
+    // their partial sums.  Every width the kernels exist for is planned and the modelled time of the plan compared
+    // (latency_cost); a width given by dnnb_net_set_latency_widths or DNNB_LAT_BN is taken as it is.  `crowding`:
+    // the block is followed by a cluster split-K kernel, whose CTAs can start (prologue, first weight tiles) while
+    // this one still runs only on SMs it leaves free -- and a cluster needs a whole group of them.
+    auto choose_latency_width = [&](size_t i, bool blk_in_bf16, bool crowding) {
+        Block &b = net->blocks[i];
+        const int forced_bn = i < net->lat_widths.size() && net->lat_widths[i] > 0 ? net->lat_widths[i] : net->knobs.lat_bn;
+        if (forced_bn > 0) {
+            b.lat_bn = forced_bn;
+            plan_block(net, i, blk_in_bf16);
+            if (b.family == DNNB_KERNEL_SIMT) {          // no tcgen05 kernel of that width: the planner's own width
+                b.lat_bn = 0;
+                plan_block(net, i, blk_in_bf16);
+            }
+            return;
+        }
+        auto cost_of = [&]() {
+            double c = latency_cost(b, net->num_sms);
+            if (c >= 0.0 && crowding) {
+                const int ctas = b.up.num_m_tiles * b.up.num_n_tiles * (b.up.splits > 1 ? b.up.splits : 1);
+                c += 2.0 * (ctas < net->num_sms ? (double)ctas / net->num_sms : 1.0);
+            }
+            return c;
+        };
+        int best_bn = 0;
+        double best = 0.0;
+        const int cands[4] = {0, 128, 64, 32};       // 0: the planner's own width (up to 256)
+        for (int c = 0; c < 4; ++c) {
+            b.lat_bn = cands[c];
+            plan_block(net, i, blk_in_bf16);
+            if (c == 0) {
+                best = cost_of();
+                if (best < 0.0) break;               // not a block of the generic kernel: nothing to choose
+                continue;
+            }
+            if (b.bn != cands[c]) continue;          // the cap did not bind: same plan as a wider candidate
+            const double cost = cost_of();
+            if (cost < 0.0) continue;
+            if (cost + 0.2 <= best) {                // a tie goes to the wider tile
+                best = cost;
+                best_bn = cands[c];
+            }
+        }
+        b.lat_bn = best_bn;
+        plan_block(net, i, blk_in_bf16);
+        if (net->knobs.verbose_plan)
+            fprintf(stderr, "dnnb plan: block %zu latency width %d (bn %d, splits %d, cluster %d%s) modelled %.1f us\n", i, best_bn,
+                    b.bn, b.up.splits, b.up.cluster_splitk, crowding ? ", crowding its successor" : "", best);
+    };
+    std::vector<char> blk_in_bf16(net->blocks.size(), 0);
     for (size_t i = 0; i < net->blocks.size(); ++i) {
         Block &b = net->blocks[i];
         b.ih = h; b.iw = w;
@@ -461,6 +513,7 @@ int dnnb_net_finalize(dnnb_net *net) {
             out_pads(b.cw, b.pool_k, b.pool_s, b.pool_same, &b.ow, &b.ppl, &pb);
             if (b.oh <= 0 || b.ow <= 0) return fail("block %zu: empty pool output", i);
         }
+        blk_in_bf16[i] = in_bf16;
         if (i == 0 && net->precision == DNNB_BF16) {
             // conv0 reads the fp32 image itself; any other tcgen05 first block gets a bf16 cast
             plan_block(net, i, false);
@@ -469,46 +522,26 @@ int dnnb_net_finalize(dnnb_net *net) {
                 if (b.family == DNNB_KERNEL_SIMT) plan_block(net, i, false);
             }
         } else if (net->knobs.latency) {
-            // Small batches: the N-tile width decides how a block is cut (tiles x K slices) and through what the slices
-            // exchange their partial sums.  Every width the kernels exist for is planned and the modelled time of the
-            // plan compared (latency_cost); DNNB_LAT_BN=n forces a cap instead.
-            const int forced_bn = i < net->lat_widths.size() && net->lat_widths[i] > 0 ? net->lat_widths[i] : net->knobs.lat_bn;
-            if (forced_bn > 0) {
-                b.lat_bn = forced_bn;
-                plan_block(net, i, in_bf16);
-                if (b.family == DNNB_KERNEL_SIMT) {          // no tcgen05 kernel of that width: the planner's own width
-                    b.lat_bn = 0;
-                    plan_block(net, i, in_bf16);
-                }
-            } else {
-                int best_bn = 0;
-                double best = 0.0;
-                const int cands[4] = {0, 128, 64, 32};       // 0: the planner's own width (up to 256)
-                for (int c = 0; c < 4; ++c) {
-                    b.lat_bn = cands[c];
-                    plan_block(net, i, in_bf16);
-                    if (c == 0) {
-                        best = latency_cost(b, net->num_sms);
-                        if (best < 0.0) break;               // not a block of the generic kernel: nothing to choose
-                        continue;
-                    }
-                    if (b.bn != cands[c]) continue;          // the cap did not bind: same plan as a wider candidate
-                    const double cost = latency_cost(b, net->num_sms);
-                    if (cost < 0.0) continue;
-                    if (cost + 0.2 <= best) {                // a tie goes to the wider tile
-                        best = cost;
-                        best_bn = cands[c];
-                    }
-                }
-                b.lat_bn = best_bn;
-                plan_block(net, i, in_bf16);
-                if (net->knobs.verbose_plan)
-                    fprintf(stderr, "dnnb plan: block %zu latency width %d (bn %d, splits %d, cluster %d) modelled %.1f us\n", i, best_bn,
-                            b.bn, b.up.splits, b.up.cluster_splitk, best);
-            }
+            choose_latency_width(i, in_bf16, false);
         } else {
             plan_block(net, i, in_bf16);
         }
+        in_bf16 = b.out_bf16;
+        h = b.oh; w = b.ow;
+    }
+    if (net->knobs.latency) {
+        // second look at the blocks that are followed by a cluster split-K kernel (a block's plan does not depend on its
+        // neighbours' plans, so one pass is enough)
+        for (size_t i = 0; i + 1 < net->blocks.size(); ++i) {
+            const Block &next = net->blocks[i + 1];
+            const bool next_cluster = (next.family == DNNB_KERNEL_UMMA_IM2COL || next.family == DNNB_KERNEL_UMMA_TILED) &&
+                                      next.up.splits > 1 && next.up.cluster_splitk;
+            if (next_cluster && !(i == 0 && net->precision == DNNB_BF16)) choose_latency_width(i, blk_in_bf16[i] != 0, true);
+        }
+    }
+    // ---- device memory, constants, prepacked weights, tensor maps
+    for (size_t i = 0; i < net->blocks.size(); ++i) {
+        Block &b = net->blocks[i];
         const size_t es_out = b.out_bf16 ? 2 : 4;
         b.out_elems = (size_t)net->B * b.oh * b.ow * b.oc;
         b.conv_out_elems = b.pool_fused ? b.out_elems : (size_t)net->B * b.ch * b.cw * b.oc;
@@ -600,8 +633,6 @@ int dnnb_net_finalize(dnnb_net *net) {
             }
         }
         net->launches += 1 + (b.pool_separate ? 1 : 0);
-        in_bf16 = b.out_bf16;
-        h = b.oh; w = b.ow;
     }
     const size_t n_in = (size_t)net->B * net->H * net->W * net->C;
     CK(cudaMalloc(&net->d_in2[0], n_in * 4));
