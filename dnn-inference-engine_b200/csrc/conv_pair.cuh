@@ -119,6 +119,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::cluster_sync_all();          // both CTAs' barriers exist before anything remote touches them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch (no-ops when the launch does not ask for it): the next kernel's CTAs may take the SMs
+    // this grid's ragged end leaves idle and run their prologue there; nothing above depends on the preceding kernel.
+    ptx::griddep_launch();
+    ptx::griddep_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)

@@ -446,7 +446,7 @@ int dnnb_net_finalize(dnnb_net *net) {
             net->knobs.latency = net->latency_override != 0;
         }
     }
-    net->pdl = net->knobs.latency && !net->knobs.no_pdl;
+    net->pdl = (net->knobs.latency || net->knobs.pdl_all) && !net->knobs.no_pdl;
     net->use_graph = net->knobs.latency && !net->knobs.no_graph;
     // ---- geometry and plan of every block (no device memory yet)
     // Latency plan: the N-tile width decides how a block is cut (tiles x K slices) and through what the slices exchange

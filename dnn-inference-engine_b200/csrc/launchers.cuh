@@ -228,8 +228,7 @@ cudaError_t launch_pair(const CUtensorMap &ma, const CUtensorMap &mb, const pair
     static bool done[64] = {};
     cudaError_t e = set_smem_once(kern, C::SMEM_BYTES, done);
     if (e != cudaSuccess) return e;
-    kern<<<grid, pairconv::kThreads, C::SMEM_BYTES, st>>>(ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
-    return cudaGetLastError();
+    return launch_ex(kern, (unsigned)grid, pairconv::kThreads, C::SMEM_BYTES, st, false, ma, mb, p);     // __cluster_dims__(2,1,1): grid is even
 }
 #define PAIR_ENTRY(BF16, OBF, MT, BN) {BF16, OBF, MT, BN, &launch_pair<BF16, OBF, MT, BN>, pairconv::Cfg<MT, BN>::STAGES, false}
 #define PAIR_ENTRY_P1(BF16, OBF, BN) {BF16, OBF, 1, BN, &launch_pair<BF16, OBF, 1, BN, true>, pairconv::Cfg<1, BN, true>::STAGES, true}

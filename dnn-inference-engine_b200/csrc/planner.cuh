@@ -46,6 +46,7 @@ struct Knobs {
     bool no_pool1_fusion = false;    // DNNB_NO_POOL1_FUSION  block 5: the stride-1 SAME pool as a separate kernel
     bool no_cluster_splitk = false;  // DNNB_NO_CLUSTER_SPLITK latency plan: split-K through the global workspace, not cluster DSMEM
     bool no_tma_store = false;       // DNNB_NO_TMA_STORE     epilogues store with per-thread st.global instead of bulk copies
+    bool pdl_all = false;            // DNNB_PDL_ALL          programmatic dependent launch in the default (throughput) plan too
     int lat_bn = 0;                  // DNNB_LAT_BN=n         latency plan: cap on the N tile for every block (default: 128 where it keeps the pools fused)
     bool verbose_plan = false;       // DNNB_VERBOSE_PLAN     print planning decisions to stderr
 };
@@ -67,7 +68,7 @@ const KnobDef g_knob_defs[] = {
     {"DNNB_PAIR_MT", false, 1, 2},         {"DNNB_PAIR_MIN_TILES", false, 0, 1 << 30}, {"DNNB_PAIR_NO_TAIL", true, 0, 1}, {"DNNB_PAIR_FORCE_TAIL", true, 0, 1},
     {"DNNB_NO_PAIR_TAIL", true, 0, 1},     {"DNNB_NO_TAIL", true, 0, 1},         {"DNNB_LAT_FUSE_NB", false, 0, 128},
     {"DNNB_SPLIT_MIN_STAGES", false, 0, 1024}, {"DNNB_NO_U8_FUSION", true, 0, 1}, {"DNNB_NO_POOL1_FUSION", true, 0, 1},
-    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_VERBOSE_PLAN", true, 0, 1}, {"DNNB_LAT_BN", false, 0, 256},
+    {"DNNB_NO_CLUSTER_SPLITK", true, 0, 1}, {"DNNB_NO_TMA_STORE", true, 0, 1},   {"DNNB_VERBOSE_PLAN", true, 0, 1}, {"DNNB_LAT_BN", false, 0, 256}, {"DNNB_PDL_ALL", true, 0, 1},
 };
 
 // Reads the switches.  `active` receives "NAME=value" for every switch that is set to something other than
@@ -140,6 +141,7 @@ int read_knobs(Knobs &k, std::string &active, std::string &err) {
     k.no_tma_store = value("DNNB_NO_TMA_STORE", 0) != 0;
     k.verbose_plan = value("DNNB_VERBOSE_PLAN", 0) != 0;
     k.lat_bn = value("DNNB_LAT_BN", 0);
+    k.pdl_all = value("DNNB_PDL_ALL", 0) != 0;
     return bad ? 1 : 0;
 }
 
