@@ -208,8 +208,44 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int m_first = p.m_base + ((m_tile * MT + mi) * 2 + (int)rank) * p.m_stride;
                 const int m = m_first + row;
                 const bool valid = m < p.M_total;
+                if constexpr (POOL1 && OUT_BF16) {
+                    // bf16 storage: 64 columns per pass, pooled as packed pairs (epilogue_pool1.cuh: store_chunk_bf16x2)
+                    auto activated = [&](int chunk, float (&v)[32]) {
+                        uint32_t raw[32];
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * kBN + chunk * 32, raw);
+                        ptx::tmem_ld_wait();
+                        const int c0 = n_tile * kBN + chunk * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0 + j);
+                            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c0 + j);
+                            v[j + 0] = fmaf(__uint_as_float(raw[j + 0]), sc.x, sh.x);
+                            v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y);
+                            v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z);
+                            v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w);
+                        }
+                        if (p.leaky) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+                        }
+                        if (p.prepool != nullptr) {            // debug dump wants the stored (rounded) values
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+                            pool1::dump_prepool(v, m, p.M_total, row < p.m_stride, p.OC, c0, p.prepool);
+                        }
+                    };
 #pragma unroll 1
-                for (int chunk = 0; chunk < kBN / 32; ++chunk) {
+                    for (int chunk = 0; chunk < kBN / 32; chunk += 2) {
+                        float v0[32], v1[32];
+                        activated(chunk, v0);
+                        activated(chunk + 1, v1);
+                        pool1::store_chunk_bf16x2(ptx::smem_u32(s_stage), v0, v1, quarter, lane, m_first, p.m_stride, p.M_total, p.H,
+                                                  p.OC, n_tile * kBN + chunk * 32, p.out, p.out_elems);
+                    }
+                }
+                constexpr int kChunks32 = (POOL1 && OUT_BF16) ? 0 : kBN / 32;       // (the packed path above took them all)
+#pragma unroll 1
+                for (int chunk = 0; chunk < kChunks32; ++chunk) {
                     uint32_t raw[32];
                     ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_COLS + mi * kBN + chunk * 32, raw);
                     ptx::tmem_ld_wait();

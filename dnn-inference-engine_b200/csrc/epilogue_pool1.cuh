@@ -79,6 +79,62 @@ __device__ __forceinline__ void store_chunk(uint32_t s_stage, const float (&v)[3
     (void)prepool;
 }
 
+// BF16 storage: the same walk on packed pairs.  v0 / v1: columns [col0, col0 + 32) and [col0 + 32, col0 + 64) of the
+// thread's row, activated (fp32).  They are rounded to bf16 here -- the reference pools the stored values -- and staged
+// as 32 words of two channels each, so that a lane owns two adjacent channels: half the staging traffic, half the
+// window-walk instructions (HMNMX2) and 4-byte instead of 2-byte stores per lane (a whole 128-byte line per row and
+// warp) for the same 64 channels.  With 2-byte stores the BF16 block 5 was epilogue-bound (tensor pipe 49 % busy).
+__device__ __forceinline__ void store_chunk_bf16x2(uint32_t s_stage, const float (&v0)[32], const float (&v1)[32], int quarter,
+                                                   int lane, int m0, int m_stride, int M_total, int H, int OC, int col0,
+                                                   void *out, size_t out_elems) {
+    const uint32_t mine = s_stage + (uint32_t)(quarter * 32 + lane) * (kPitch * 4);
+    auto pack = [](float a, float b) {
+        const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<const uint32_t *>(&t);
+    };
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + 4 * j), "r"(pack(v0[2 * j], v0[2 * j + 1])),
+                     "r"(pack(v0[2 * j + 2], v0[2 * j + 3])), "r"(pack(v0[2 * j + 4], v0[2 * j + 5])),
+                     "r"(pack(v0[2 * j + 6], v0[2 * j + 7])) : "memory");
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + 64 + 4 * j), "r"(pack(v1[2 * j], v1[2 * j + 1])),
+                     "r"(pack(v1[2 * j + 2], v1[2 * j + 3])), "r"(pack(v1[2 * j + 4], v1[2 * j + 5])),
+                     "r"(pack(v1[2 * j + 6], v1[2 * j + 7])) : "memory");
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int r0 = quarter * 32;
+    constexpr int kRows = 32 + kHalo + 1;
+    __nv_bfloat162 x[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        uint32_t w;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(s_stage + (uint32_t)(min(r0 + i, 127) * kPitch + lane) * 4));
+        x[i] = *reinterpret_cast<const __nv_bfloat162 *>(&w);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // everybody has its rows: the staging area may be rewritten
+    const int m = m0 + r0;
+    const int hw = m % (H * kW);
+    int h = hw / kW, w = hw - h * kW;
+    int wi = w;
+#pragma unroll
+    for (int i = 0; i < 32 + kW; ++i) {
+        if (wi + 1 < kW) x[i] = __hmax2(x[i], x[i + 1]);
+        if (++wi == kW) wi = 0;
+    }
+    const int col = col0 + 2 * lane;
+    if (col >= OC) return;
+    const int n_rows = min(min(32, m_stride - r0), M_total - m);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i < n_rows) {
+            const __nv_bfloat162 a = (h + 1 < H) ? __hmax2(x[i], x[i + kW]) : x[i];
+            *reinterpret_cast<__nv_bfloat162 *>(ptx::out_at<__nv_bfloat16>(out, (size_t)(m + i) * OC + col, 2, out_elems, 18)) = a;
+        }
+        if (++w == kW) { w = 0; if (++h == H) h = 0; }
+    }
+}
+
 // The 2x2 stride-2 pool over an im2col tile that is whole PAIRS of image rows (m_stride = 2k W pixels, W even;
 // small batches under the latency plan, where spatial tiles would be mostly padding): pooled pixel (pr, pc) of the
 // tile is the maximum of tile rows 2 pr W + 2 pc + {0, 1, W, W + 1}.  `s_stage` holds [128][kPitch] activated values
